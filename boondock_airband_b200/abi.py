@@ -70,6 +70,7 @@ class EngineDesc(C.Structure):
         ("devices", C.POINTER(DeviceDesc)),
         ("max_batches_per_step", C.c_int32),
         ("flags", C.c_uint32),
+        ("ring_bytes", C.c_uint64),
     ]
 
 
@@ -180,6 +181,7 @@ class EngineCfg:
     cuda_device: int = 0
     max_batches_per_step: int = 0
     flags: int = 0
+    ring_bytes: int = 0  # 0 = the reference's MIN_BUF_SIZE
 
     @property
     def wave_batch(self) -> int:
@@ -223,5 +225,5 @@ def build_desc(cfg: EngineCfg):
                              int(d.centerfreq), int(d.tau), len(d.channels), chans)
     keep.append(devs)
     desc = EngineDesc(ABI_VERSION, cfg.fft_size, cfg.wave_rate, cfg.fm_demod, cfg.cuda_device, len(cfg.devices), devs,
-                      cfg.max_batches_per_step, cfg.flags)
+                      cfg.max_batches_per_step, cfg.flags, cfg.ring_bytes)
     return desc, keep

@@ -1,0 +1,1200 @@
+/*
+ * ba_engine.cu — host side of the B200 channelize-and-demodulate engine: the extern "C" boundary of include/ba_cuda.h.
+ *
+ * It plays the role of the body of demodulate() (boondock_airband.cpp:383-737) for the inputs handed to it:
+ *   ring availability + hop arithmetic   .cpp:394-399, 418-424, 735   -> plan_step()
+ *   circbuffer_append()                  input-helpers.cpp:37-63      -> ba_cuda_submit() / ba_cuda_commit()
+ *   convert + window + FFT + bin pick    .cpp:426-516                 -> K1 (channelize.cu), one launch for all inputs
+ *   per-channel loop                     .cpp:518-672                 -> K2 (demod.cu), one launch for all channels
+ *   hand-off waveavail / Signal::send    .cpp:673-679, 728            -> ba_cuda_collect()
+ * One CUDA stream; every step's descriptors go up in one copy, its results come back in a few large ones.
+ * With AFC enabled on an input (channel_t.afc > 0, .cpp:650-654) that input's bins can move after every batch, so
+ * its K1/K2 launches alternate batch by batch ("phases"); all other inputs run a whole step in one K1 + one K2.
+ *
+ * There is no CPU implementation behind this file: without a CUDA device ba_cuda_create() returns BA_ERR_NO_DEVICE.
+ */
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "ba_kernels.h"
+#include "host_model.h"
+
+#define BA_MIN_BUF_SIZE 2560000 /* MIN_BUF_SIZE, boondock_airband.h:64 */
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (cudaError_t)(call);                                                          \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(BA_ERR_CUDA, "%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+uint32_t pow2_at_least(uint64_t v) {
+    uint32_t p = 1;
+    while (p < v)
+        p <<= 1;
+    return p;
+}
+
+struct ExtChunk {
+    const unsigned char* p;
+    size_t n;
+};
+
+struct Dev {
+    ba_device_desc cfg;
+    std::vector<ba_channel_desc> chans;
+    int C = 0, c_pad = 0;
+    size_t sample_bytes = 0; /* one complex sample */
+    size_t hop_bytes = 0, frame_bytes = 0;
+    bool any_afc = false, any_iq = false;
+    int first_chan = 0;
+    /* host ring = input_t.buffer */
+    std::mutex lock;
+    unsigned char* ring = nullptr;
+    size_t buf_size = 0, mirror = 0, bufs = 0, bufe = 0;
+    uint64_t overflow_count = 0;
+    std::vector<ExtChunk> ext;
+    /* stream in HBM */
+    unsigned char* d_buf[2] = {nullptr, nullptr};
+    size_t d_cap = 0;
+    int cur = 0;
+    size_t have = 0;       /* bytes valid in d_buf[cur] */
+    uint64_t base_off = 0; /* stream offset of d_buf[cur][0] */
+    const unsigned char* attached = nullptr;
+    size_t attached_cap = 0, attached_valid = 0;
+    uint64_t frames_done = 0, batches_done = 0;
+    bool injected = false;
+    /* picks, bins */
+    float2* d_picks = nullptr;
+    uint32_t ring_len = 0;
+    uint32_t* d_bins = nullptr;
+    float2* d_spectrum = nullptr;
+    std::vector<uint32_t> base_bins;
+    /* arena offsets (elements) */
+    size_t wave_off = 0, iq_off = 0, status_off = 0;
+    /* plan of the current step */
+    int step_frames = 0, step_batches = 0;
+    uint64_t step_frame0 = 0, step_batch0 = 0;
+};
+
+struct Slot {
+    float* d_wave = nullptr;
+    float* h_wave = nullptr;
+    float2* d_iq = nullptr;
+    float2* h_iq = nullptr;
+    uint8_t* d_trace = nullptr;
+    uint8_t* h_trace = nullptr;
+    ba_channel_status* d_status = nullptr;
+    ba_channel_status* h_status = nullptr;
+    unsigned char* d_desc = nullptr;
+    unsigned char* h_desc = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_done = nullptr;
+    std::vector<cudaEvent_t> ev_k; /* 3 per phase: before K1, between, after K2 */
+    int phases = 0;
+    int ticket = -1;
+    bool busy = false;
+    std::vector<int> n_batches; /* per device */
+    std::vector<uint64_t> frames_done;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;
+};
+
+}  // namespace
+
+struct ba_engine {
+    int fft_size = 0, wave_rate = 0, B = 0, fm_demod = 0, cuda_device = 0, max_batches = 0;
+    uint32_t flags = 0;
+    int sm_count = 0, smem_optin = 0;
+    std::vector<Dev*> dev;
+    int total_channels = 0, max_channels = 0;
+    int stride = 0; /* max_batches*B + E */
+    bool any_iq = false, any_afc = false;
+    cudaStream_t stream = nullptr;
+    float* d_window = nullptr;
+    float2* d_twiddle = nullptr;
+    float* d_sincos = nullptr;
+    std::vector<float> window;
+    ba::K2Chan* d_chan = nullptr;
+    ba::K2State* d_state = nullptr;
+    ba::K2Ctcss* d_ctcss = nullptr;
+    int32_t* d_order = nullptr;
+    std::vector<ba::K2Chan> h_chan;
+    std::vector<ba_channel_info> info;
+    Slot slot[2];
+    int next_ticket = 0;
+    uint64_t launches = 0;
+    int tile_frames = 0, raw_bytes = 0, k1_ctas_per_sm = 1;
+    size_t desc_bytes = 0;
+    int max_phases = 1;
+};
+
+namespace {
+
+void free_engine(ba_engine* e) {
+    if (!e)
+        return;
+    if (e->stream)
+        cudaStreamSynchronize(e->stream);
+    for (Dev* d : e->dev) {
+        if (!d)
+            continue;
+        if (d->ring)
+            cudaFreeHost(d->ring);
+        cudaFree(d->d_buf[0]);
+        cudaFree(d->d_buf[1]);
+        cudaFree(d->d_picks);
+        cudaFree(d->d_bins);
+        cudaFree(d->d_spectrum);
+        delete d;
+    }
+    for (Slot& s : e->slot) {
+        cudaFree(s.d_wave);
+        cudaFree(s.d_iq);
+        cudaFree(s.d_trace);
+        cudaFree(s.d_status);
+        cudaFree(s.d_desc);
+        if (s.h_wave)
+            cudaFreeHost(s.h_wave);
+        if (s.h_iq)
+            cudaFreeHost(s.h_iq);
+        if (s.h_trace)
+            cudaFreeHost(s.h_trace);
+        if (s.h_status)
+            cudaFreeHost(s.h_status);
+        if (s.h_desc)
+            cudaFreeHost(s.h_desc);
+        if (s.ev_begin)
+            cudaEventDestroy(s.ev_begin);
+        if (s.ev_done)
+            cudaEventDestroy(s.ev_done);
+        for (cudaEvent_t ev : s.ev_k)
+            cudaEventDestroy(ev);
+    }
+    cudaFree(e->d_window);
+    cudaFree(e->d_twiddle);
+    cudaFree(e->d_sincos);
+    cudaFree(e->d_chan);
+    cudaFree(e->d_state);
+    cudaFree(e->d_ctcss);
+    cudaFree(e->d_order);
+    if (e->stream)
+        cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+/* frames the reference's availability test admits for a stream of `total` bytes (.cpp:418-424 with FFT_BATCH 1):
+ * frame f runs while total - f*bps >= bps + fft_size*bytes_per_sample*2 */
+uint64_t frames_admitted(const Dev& d, uint64_t total) {
+    const uint64_t need = d.hop_bytes + d.frame_bytes;
+    if (total < need)
+        return 0;
+    return (total - need) / d.hop_bytes + 1;
+}
+
+/* fills K2Chan constants + initial K2State of one channel; mirrors parse_channels (config.cpp:312-729) */
+int setup_channel(ba_engine* e, Dev& d, int ci, ba::K2Chan& k, ba::K2State& st, ba::K2Ctcss* ctcss_pool, int& n_ctcss, ba_channel_info& in) {
+    using namespace ba;
+    const ba_channel_desc& cd = d.chans[ci];
+    const int R = e->wave_rate, N = e->fft_size;
+    memset(&k, 0, sizeof(k));
+    memset(&st, 0, sizeof(st));
+    memset(&in, 0, sizeof(in));
+    if (cd.modulation != BA_MOD_AM && cd.modulation != BA_MOD_NFM)
+        return fail(BA_ERR_BAD_ARG, "channel %d: unknown modulation %d", ci, cd.modulation);
+    k.col = (uint32_t)ci;
+    k.picks = d.d_picks;
+    k.ring_mask = d.ring_len - 1;
+    k.c_pad = (uint32_t)d.c_pad;
+    k.bin = d.d_bins + ci;
+    k.fft_size = N;
+    k.modulation = cd.modulation;
+    k.afc = cd.afc & 0xff;
+    k.has_iq_outputs = cd.has_iq_outputs ? 1 : 0;
+    k.needs_raw_iq = (cd.modulation == BA_MOD_NFM || cd.bandwidth > 0 || cd.has_iq_outputs) ? 1 : 0; /* config.cpp:162,596,674-680 */
+    k.fm_demod = e->fm_demod;
+    k.ampfactor = cd.ampfactor;
+    float alpha = model::alpha_default(R);
+    if (d.cfg.tau_us >= 0)
+        alpha = model::alpha_from_tau_us(R, d.cfg.tau_us);
+    if (cd.tau_us >= 0)
+        alpha = model::alpha_from_tau_us(R, cd.tau_us);
+    k.alpha = alpha;
+    /* Squelch defaults (squelch.cpp:36-70), then the settings in the order parse_channels applies them (config.cpp:437-515) */
+    k.manual = 0;
+    k.manual_level = -1.0f;
+    k.ratio = model::snr_ratio(9.54f);
+    if (cd.squelch_threshold_dbfs < 0) {
+        const float level = model::dbfs_to_level((float)cd.squelch_threshold_dbfs, N);
+        if (level > 0) {
+            k.manual = 1;
+            k.manual_level = level;
+        }
+    }
+    if (cd.squelch_snr_threshold >= 0) {
+        k.manual = 0;
+        k.ratio = model::snr_ratio(cd.squelch_snr_threshold);
+    }
+    k.flappy_ratio = k.ratio * 0.9f;
+    if (cd.notch > 0) {
+        float dd[3];
+        const float q = cd.notch_q == 0.0f ? 10.0f : cd.notch_q;
+        if (model::notch_design(cd.notch, (float)R, q, dd)) {
+            k.notch_on = 1;
+            k.nd0 = dd[0], k.nd1 = dd[1], k.nd2 = dd[2];
+        }
+    }
+    if (cd.bandwidth > 0) {
+        float yc[2], gain;
+        if (model::lowpass_design((float)cd.bandwidth / 2, (float)R, yc, &gain)) {
+            k.lp_on = 1;
+            k.lp_c0 = yc[0], k.lp_c1 = yc[1], k.lp_gain = gain;
+        }
+    }
+    k.base_bin = model::bin_index(cd.frequency, d.cfg.sample_rate, d.cfg.centerfreq, N);
+    d.base_bins[ci] = k.base_bin;
+    if (k.needs_raw_iq)
+        k.dm_dphi = model::derotation_step(cd.frequency, d.cfg.centerfreq, d.cfg.sample_rate, R);
+    if (cd.ctcss > 0) { /* Squelch::set_ctcss_freq, squelch.cpp:106-116 */
+        K2Ctcss& c = ctcss_pool[n_ctcss];
+        memset(&c, 0, sizeof(c));
+        c.win_fast = (int)((float)R * 0.05);
+        c.win_slow = (int)((float)R * 0.4);
+        c.n_fast = model::tone_bank(cd.ctcss, (float)R, c.win_fast, c.coeff_fast);
+        c.n_slow = model::tone_bank(cd.ctcss, (float)R, c.win_slow, c.coeff_slow);
+        k.ctcss = e->d_ctcss + n_ctcss;
+        n_ctcss++;
+        in.ctcss_fast_tones = c.n_fast;
+        in.ctcss_slow_tones = c.n_slow;
+        in.ctcss_fast_window = c.win_fast;
+        in.ctcss_slow_window = c.win_slow;
+    }
+    /* initial state: Squelch constructor (squelch.cpp:36-70), channel_t/freq_t defaults (config.cpp:276-286,319-334) */
+    st.noise = 5.0f;
+    st.pre_full = st.pre_cap = st.post_full = st.post_cap = 0.001f;
+    st.next = st.cur = BA_SQ_CLOSED;
+    st.count16 = 15; /* sample_count_ starts at (size_t)-1: the very first sample updates the noise floor */
+    st.head = 0;
+    st.tail = 1;
+    st.prev_waveout = 0.5f;
+    st.agcavgfast = 0.5f;
+    st.axcindicate = BA_NO_SIGNAL;
+    for (int i = 0; i < BA_E; i++)
+        st.waveout_tail[i] = 0.5f;
+
+    in.bin = k.base_bin;
+    in.dm_dphi = k.dm_dphi;
+    in.needs_raw_iq = k.needs_raw_iq;
+    in.alpha = k.alpha;
+    in.squelch_ratio = k.ratio;
+    in.manual_level = k.manual ? k.manual_level : 0.0f;
+    in.notch_enabled = k.notch_on;
+    in.notch_d[0] = k.nd0, in.notch_d[1] = k.nd1, in.notch_d[2] = k.nd2;
+    in.lowpass_enabled = k.lp_on;
+    in.lowpass_ycoeffs[0] = k.lp_c0, in.lowpass_ycoeffs[1] = k.lp_c1;
+    in.lowpass_gain = k.lp_gain;
+    return BA_OK;
+}
+
+/* tile shape of K1 for this engine: as many frames per tile as fit the shared-memory budget, bounded so that
+ * a step still spreads over the SMs */
+int choose_tiles(ba_engine* e) {
+    const int N = e->fft_size;
+    size_t max_hop = 0, max_frame = 0;
+    for (Dev* d : e->dev) {
+        max_hop = std::max(max_hop, d->hop_bytes);
+        max_frame = std::max(max_frame, d->frame_bytes);
+    }
+    const int groups = ba::k1_groups(N);
+    const int fixed = ba::k1_smem_bytes(N, 0, e->max_channels);
+    /* budget: half an SM's shared memory at most so that two CTAs can be resident when registers allow */
+    const int budget = std::min(e->smem_optin, 100 * 1024);
+    int tf = 4 * groups;
+    for (;;) {
+        const size_t raw = (size_t)(tf - 1) * max_hop + max_frame + 32;
+        if ((size_t)fixed + raw <= (size_t)budget || tf <= groups)
+            break;
+        tf -= groups;
+    }
+    if (tf < 1)
+        tf = 1;
+    size_t raw = (size_t)(tf - 1) * max_hop + max_frame + 32;
+    raw = (raw + 15) & ~(size_t)15;
+    if ((size_t)fixed + raw > (size_t)e->smem_optin)
+        return fail(BA_ERR_NOMEM, "K1 needs %zu bytes of shared memory per CTA, the device offers %d", (size_t)fixed + raw, e->smem_optin);
+    e->tile_frames = tf;
+    e->raw_bytes = (int)raw;
+    return BA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ba_cuda_last_error(void) {
+    return g_err;
+}
+
+int ba_cuda_visible_devices(void) {
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess)
+        return fail(BA_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(err));
+    return n;
+}
+
+void ba_cuda_destroy(ba_engine* e) {
+    free_engine(e);
+}
+
+int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
+    using namespace ba;
+    if (!desc || !out)
+        return fail(BA_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    if (desc->abi_version != BA_CUDA_ABI_VERSION)
+        return fail(BA_ERR_BAD_ARG, "ABI version %d, library speaks %d", desc->abi_version, BA_CUDA_ABI_VERSION);
+    const int N = desc->fft_size;
+    if (N < 256 || N > 8192 || (N & (N - 1)))
+        return fail(BA_ERR_BAD_SIZE, "fft_size %d is not a power of two in 256..8192", N);
+    if (desc->wave_rate <= 0 || desc->wave_rate % 8)
+        return fail(BA_ERR_BAD_ARG, "wave_rate %d", desc->wave_rate);
+    if (desc->device_count <= 0 || !desc->devices)
+        return fail(BA_ERR_BAD_ARG, "no devices");
+    int visible = 0;
+    cudaError_t ce = cudaGetDeviceCount(&visible);
+    if (ce != cudaSuccess || visible <= 0)
+        return fail(BA_ERR_NO_DEVICE, "no CUDA device (%s); this engine has no CPU path", ce != cudaSuccess ? cudaGetErrorString(ce) : "count 0");
+    if (desc->cuda_device < 0 || desc->cuda_device >= visible)
+        return fail(BA_ERR_NO_DEVICE, "cuda_device %d of %d", desc->cuda_device, visible);
+    if (cudaSetDevice(desc->cuda_device) != cudaSuccess)
+        return fail(BA_ERR_NO_DEVICE, "cudaSetDevice(%d) failed", desc->cuda_device);
+
+    ba_engine* e = new (std::nothrow) ba_engine();
+    if (!e)
+        return fail(BA_ERR_NOMEM, "host allocation");
+    struct Guard {
+        ba_engine* e;
+        ~Guard() {
+            if (e)
+                free_engine(e);
+        }
+    } guard{e};
+
+    e->fft_size = N;
+    e->wave_rate = desc->wave_rate;
+    e->B = desc->wave_rate / 8;
+    e->fm_demod = desc->fm_demod;
+    e->cuda_device = desc->cuda_device;
+    e->max_batches = desc->max_batches_per_step > 0 ? desc->max_batches_per_step : 8;
+    e->flags = desc->flags;
+    e->stride = e->max_batches * e->B + BA_E;
+    CU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, desc->cuda_device));
+    CU(cudaDeviceGetAttribute(&e->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, desc->cuda_device));
+    CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+
+    /* window, twiddles, sine/cosine table */
+    e->window.resize(N);
+    model::window7(N, e->window.data());
+    std::vector<float2> tw(N);
+    model::twiddles(N, tw.data());
+    float sc[514];
+    model::sincos_table(sc);
+    CU(cudaMalloc((void**)&e->d_window, sizeof(float) * N));
+    CU(cudaMalloc((void**)&e->d_twiddle, sizeof(float2) * N));
+    CU(cudaMalloc((void**)&e->d_sincos, sizeof(sc)));
+    CU(cudaMemcpy(e->d_window, e->window.data(), sizeof(float) * N, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->d_twiddle, tw.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->d_sincos, sc, sizeof(sc), cudaMemcpyHostToDevice));
+
+    const size_t ring_min = desc->ring_bytes > 0 ? (size_t)desc->ring_bytes : (size_t)BA_MIN_BUF_SIZE;
+    const uint64_t frames_cap = (uint64_t)(e->max_batches + 1) * e->B + BA_E;
+    int n_ctcss = 0;
+    for (int di = 0; di < desc->device_count; di++) {
+        const ba_device_desc& dd = desc->devices[di];
+        if (dd.channel_count <= 0 || !dd.channels)
+            return fail(BA_ERR_BAD_ARG, "device %d has no channels", di);
+        int want_bps = dd.sample_format == BA_SFMT_S16 ? 2 : (dd.sample_format == BA_SFMT_F32 ? 4 : 1);
+        if (dd.sample_format < BA_SFMT_U8 || dd.sample_format > BA_SFMT_F32 || dd.bytes_per_sample != want_bps)
+            return fail(BA_ERR_BAD_ARG, "device %d: sample format %d with %d bytes per sample", di, dd.sample_format, dd.bytes_per_sample);
+        if (dd.sample_rate <= e->wave_rate || !(dd.fullscale > 0))
+            return fail(BA_ERR_BAD_ARG, "device %d: sample_rate %d, fullscale %g", di, dd.sample_rate, (double)dd.fullscale);
+        Dev* d = new (std::nothrow) Dev();
+        if (!d)
+            return fail(BA_ERR_NOMEM, "host allocation");
+        e->dev.push_back(d);
+        d->cfg = dd;
+        d->chans.assign(dd.channels, dd.channels + dd.channel_count);
+        d->cfg.channels = nullptr;
+        d->C = dd.channel_count;
+        d->c_pad = (d->C + 3) & ~3;
+        d->sample_bytes = 2 * (size_t)dd.bytes_per_sample;
+        d->hop_bytes = d->sample_bytes * (size_t)round((double)dd.sample_rate / (double)e->wave_rate); /* .cpp:418 */
+        d->frame_bytes = d->sample_bytes * (size_t)N;
+        d->first_chan = e->total_channels;
+        e->total_channels += d->C;
+        e->max_channels = std::max(e->max_channels, d->C);
+        for (const ba_channel_desc& c : d->chans) {
+            if (c.afc & 0xff)
+                d->any_afc = true;
+            if (c.has_iq_outputs)
+                d->any_iq = true;
+            if (c.ctcss > 0)
+                n_ctcss++;
+        }
+        e->any_afc |= d->any_afc;
+        e->any_iq |= d->any_iq;
+        /* host ring, config.cpp:796-805 */
+        d->buf_size = model::ring_bytes(ring_min, dd.bytes_per_sample, dd.sample_rate, e->wave_rate);
+        d->mirror = d->frame_bytes;
+        if (cudaHostAlloc((void**)&d->ring, d->buf_size + d->mirror, cudaHostAllocDefault) != cudaSuccess)
+            return fail(BA_ERR_NOMEM, "pinned ring of %zu bytes", d->buf_size + d->mirror);
+        memset(d->ring, 0, d->buf_size + d->mirror);
+        /* HBM: stream window (two halves), pick ring, bins */
+        d->d_cap = (size_t)(frames_cap + 2) * d->hop_bytes + 2 * d->frame_bytes + 64;
+        d->ring_len = pow2_at_least(frames_cap + BA_E);
+        if (cudaMalloc((void**)&d->d_buf[0], d->d_cap) != cudaSuccess || cudaMalloc((void**)&d->d_buf[1], d->d_cap) != cudaSuccess ||
+            cudaMalloc((void**)&d->d_picks, sizeof(float2) * (size_t)d->ring_len * d->c_pad) != cudaSuccess ||
+            cudaMalloc((void**)&d->d_bins, sizeof(uint32_t) * d->c_pad) != cudaSuccess)
+            return fail(BA_ERR_NOMEM, "device memory for input %d", di);
+        CU(cudaMemset(d->d_picks, 0, sizeof(float2) * (size_t)d->ring_len * d->c_pad));
+        if (d->any_afc) {
+            if (cudaMalloc((void**)&d->d_spectrum, sizeof(float2) * N) != cudaSuccess)
+                return fail(BA_ERR_NOMEM, "device memory for input %d", di);
+            CU(cudaMemset(d->d_spectrum, 0, sizeof(float2) * N));
+        }
+        d->base_bins.resize(d->C);
+    }
+    if (e->any_afc)
+        e->max_phases = e->max_batches + 1;
+
+    /* per-channel constants and state */
+    const int TC = e->total_channels;
+    e->h_chan.resize(TC);
+    e->info.resize(TC);
+    std::vector<K2State> h_state(TC);
+    std::vector<K2Ctcss> h_ctcss(std::max(1, n_ctcss));
+    CU(cudaMalloc((void**)&e->d_chan, sizeof(K2Chan) * TC));
+    CU(cudaMalloc((void**)&e->d_state, sizeof(K2State) * TC));
+    CU(cudaMalloc((void**)&e->d_ctcss, sizeof(K2Ctcss) * std::max(1, n_ctcss)));
+    CU(cudaMalloc((void**)&e->d_order, sizeof(int32_t) * TC));
+    int used_ctcss = 0;
+    for (size_t di = 0; di < e->dev.size(); di++) {
+        Dev& d = *e->dev[di];
+        for (int ci = 0; ci < d.C; ci++) {
+            const int gi = d.first_chan + ci;
+            int rc = setup_channel(e, d, ci, e->h_chan[gi], h_state[gi], h_ctcss.data(), used_ctcss, e->info[gi]);
+            if (rc != BA_OK)
+                return rc;
+            e->h_chan[gi].dev = (int32_t)di;
+        }
+        std::vector<uint32_t> bins(d.c_pad, 0);
+        std::copy(d.base_bins.begin(), d.base_bins.end(), bins.begin());
+        CU(cudaMemcpy(d.d_bins, bins.data(), sizeof(uint32_t) * d.c_pad, cudaMemcpyHostToDevice));
+    }
+    /* launch order: group channels of one kind together (plain AM, filtered/NFM, CTCSS) so that the lanes of a warp run the same code */
+    {
+        std::vector<int32_t> order(TC);
+        for (int i = 0; i < TC; i++)
+            order[i] = i;
+        auto kind = [&](int i) {
+            const K2Chan& k = e->h_chan[i];
+            return (k.ctcss ? 4 : 0) + (k.modulation == BA_MOD_NFM ? 2 : 0) + (k.needs_raw_iq ? 1 : 0);
+        };
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return kind(a) < kind(b); });
+        CU(cudaMemcpy(e->d_order, order.data(), sizeof(int32_t) * TC, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemcpy(e->d_chan, e->h_chan.data(), sizeof(K2Chan) * TC, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->d_state, h_state.data(), sizeof(K2State) * TC, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->d_ctcss, h_ctcss.data(), sizeof(K2Ctcss) * std::max(1, n_ctcss), cudaMemcpyHostToDevice));
+
+    /* output arenas, two slots */
+    {
+        size_t wave = 0, status = 0;
+        for (Dev* d : e->dev) {
+            d->wave_off = wave;
+            d->iq_off = wave;
+            d->status_off = status;
+            wave += (size_t)d->C * e->stride;
+            status += (size_t)d->C * e->max_batches;
+        }
+        const size_t nd = e->dev.size();
+        e->desc_bytes = (size_t)e->max_phases * nd * (sizeof(K1Device) + sizeof(K2Dyn));
+        for (Slot& s : e->slot) {
+            if (cudaMalloc((void**)&s.d_wave, sizeof(float) * wave) != cudaSuccess || cudaHostAlloc((void**)&s.h_wave, sizeof(float) * wave, cudaHostAllocDefault) != cudaSuccess ||
+                cudaMalloc((void**)&s.d_status, sizeof(ba_channel_status) * status) != cudaSuccess ||
+                cudaHostAlloc((void**)&s.h_status, sizeof(ba_channel_status) * status, cudaHostAllocDefault) != cudaSuccess ||
+                cudaMalloc((void**)&s.d_desc, e->desc_bytes) != cudaSuccess || cudaHostAlloc((void**)&s.h_desc, e->desc_bytes, cudaHostAllocDefault) != cudaSuccess)
+                return fail(BA_ERR_NOMEM, "output arena of %zu floats", wave);
+            CU(cudaMemset(s.d_wave, 0, sizeof(float) * wave));
+            memset(s.h_wave, 0, sizeof(float) * wave);
+            if (e->any_iq) {
+                if (cudaMalloc((void**)&s.d_iq, sizeof(float2) * wave) != cudaSuccess || cudaHostAlloc((void**)&s.h_iq, sizeof(float2) * wave, cudaHostAllocDefault) != cudaSuccess)
+                    return fail(BA_ERR_NOMEM, "iq_out arena");
+                CU(cudaMemset(s.d_iq, 0, sizeof(float2) * wave));
+            }
+            if (e->flags & BA_FLAG_TRACE) {
+                if (cudaMalloc((void**)&s.d_trace, wave) != cudaSuccess || cudaHostAlloc((void**)&s.h_trace, wave, cudaHostAllocDefault) != cudaSuccess)
+                    return fail(BA_ERR_NOMEM, "trace arena");
+                CU(cudaMemset(s.d_trace, 0, wave));
+            }
+            CU(cudaEventCreate(&s.ev_begin));
+            CU(cudaEventCreate(&s.ev_done));
+            s.ev_k.resize(3 * (size_t)e->max_phases);
+            for (cudaEvent_t& ev : s.ev_k)
+                CU(cudaEventCreate(&ev));
+            s.n_batches.assign(nd, 0);
+            s.frames_done.assign(nd, 0);
+        }
+    }
+    int rc = choose_tiles(e);
+    if (rc != BA_OK)
+        return rc;
+    CU(cudaStreamSynchronize(e->stream));
+    guard.e = nullptr;
+    *out = e;
+    return BA_OK;
+}
+
+static Dev* get_dev(ba_engine* e, int dev) {
+    if (!e || dev < 0 || dev >= (int)e->dev.size()) {
+        fail(BA_ERR_BAD_ARG, "bad engine or device index %d", dev);
+        return nullptr;
+    }
+    return e->dev[dev];
+}
+
+int ba_cuda_input_ring(ba_engine* e, int dev, unsigned char** buffer, size_t* buf_size, size_t* mirror_bytes) {
+    Dev* d = get_dev(e, dev);
+    if (!d)
+        return BA_ERR_BAD_ARG;
+    if (buffer)
+        *buffer = d->ring;
+    if (buf_size)
+        *buf_size = d->buf_size;
+    if (mirror_bytes)
+        *mirror_bytes = d->mirror;
+    return BA_OK;
+}
+
+/* bytes waiting in the ring, as demodulate() computes them (.cpp:394-399) */
+static size_t ring_available(const Dev& d) {
+    return d.bufe >= d.bufs ? d.bufe - d.bufs : d.buf_size - d.bufs + d.bufe;
+}
+
+int ba_cuda_submit(ba_engine* e, int dev, const void* iq, size_t len) {
+    Dev* d = get_dev(e, dev);
+    if (!d || (!iq && len))
+        return fail(BA_ERR_BAD_ARG, "bad argument");
+    if (len == 0)
+        return BA_OK;
+    if (d->attached)
+        return fail(BA_ERR_STATE, "input %d reads a device-resident stream", dev);
+    std::lock_guard<std::mutex> g(d->lock);
+    /* unlike circbuffer_append (which overwrites unread data and counts an overflow) the caller is told */
+    if (len >= d->buf_size - ring_available(*d)) {
+        d->overflow_count++;
+        return fail(BA_ERR_OVERRUN, "input %d: ring full (%zu bytes waiting, %zu offered)", dev, ring_available(*d), len);
+    }
+    const unsigned char* buf = (const unsigned char*)iq;
+    const size_t space_left = d->buf_size - d->bufe;
+    if (space_left >= len) {
+        memcpy(d->ring + d->bufe, buf, len);
+        if (d->bufe == 0)
+            memcpy(d->ring + d->buf_size, d->ring, std::min(len, d->mirror));
+    } else {
+        memcpy(d->ring + d->bufe, buf, space_left);
+        memcpy(d->ring, buf + space_left, len - space_left);
+        memcpy(d->ring + d->buf_size, d->ring, std::min(len - space_left, d->mirror));
+    }
+    d->bufe = (d->bufe + len) % d->buf_size;
+    return BA_OK;
+}
+
+int ba_cuda_commit(ba_engine* e, int dev, size_t len) {
+    Dev* d = get_dev(e, dev);
+    if (!d)
+        return BA_ERR_BAD_ARG;
+    if (d->attached)
+        return fail(BA_ERR_STATE, "input %d reads a device-resident stream", dev);
+    std::lock_guard<std::mutex> g(d->lock);
+    if (len >= d->buf_size - ring_available(*d)) {
+        d->overflow_count++;
+        return fail(BA_ERR_OVERRUN, "input %d: ring full", dev);
+    }
+    d->bufe = (d->bufe + len) % d->buf_size;
+    return BA_OK;
+}
+
+int ba_cuda_submit_external(ba_engine* e, int dev, const void* iq, size_t len) {
+    Dev* d = get_dev(e, dev);
+    if (!d || (!iq && len))
+        return fail(BA_ERR_BAD_ARG, "bad argument");
+    if (d->attached)
+        return fail(BA_ERR_STATE, "input %d reads a device-resident stream", dev);
+    if (len == 0)
+        return BA_OK;
+    std::lock_guard<std::mutex> g(d->lock);
+    if (ring_available(*d))
+        return fail(BA_ERR_STATE, "input %d: ring data pending; do not mix ring and external submissions within a step", dev);
+    d->ext.push_back(ExtChunk{(const unsigned char*)iq, len});
+    return BA_OK;
+}
+
+int ba_cuda_attach_device_stream(ba_engine* e, int dev, const void* d_iq, size_t capacity_bytes) {
+    Dev* d = get_dev(e, dev);
+    if (!d || !d_iq)
+        return fail(BA_ERR_BAD_ARG, "bad argument");
+    if (d->frames_done || d->have)
+        return fail(BA_ERR_STATE, "input %d already consumed data", dev);
+    d->attached = (const unsigned char*)d_iq;
+    d->attached_cap = capacity_bytes;
+    d->attached_valid = 0;
+    return BA_OK;
+}
+
+int ba_cuda_advance_device_stream(ba_engine* e, int dev, size_t bytes) {
+    Dev* d = get_dev(e, dev);
+    if (!d)
+        return BA_ERR_BAD_ARG;
+    if (!d->attached)
+        return fail(BA_ERR_STATE, "input %d has no device-resident stream", dev);
+    if (d->attached_valid + bytes > d->attached_cap)
+        return fail(BA_ERR_BAD_ARG, "input %d: %zu + %zu bytes exceed the attached %zu", dev, d->attached_valid, bytes, d->attached_cap);
+    d->attached_valid += bytes;
+    return BA_OK;
+}
+
+/* frames this input may run in the coming step without overflowing its pick ring / output rows */
+static uint64_t frame_room(const ba_engine* e, const Dev& d) {
+    const uint64_t limit = (d.batches_done + (uint64_t)e->max_batches) * e->B + BA_E + e->B - 1;
+    return limit > d.frames_done ? limit - d.frames_done : 0;
+}
+
+int ba_cuda_process(ba_engine* e) {
+    using namespace ba;
+    if (!e)
+        return fail(BA_ERR_BAD_ARG, "null engine");
+    const int ticket = e->next_ticket;
+    Slot& s = e->slot[ticket & 1];
+    if (s.busy) {
+        /* the slot's previous ticket was never collected: its results are about to be replaced */
+        CU(cudaEventSynchronize(s.ev_done));
+        s.busy = false;
+    }
+    const size_t nd = e->dev.size();
+    const int B = e->B;
+    s.h2d_bytes = s.d2h_bytes = 0;
+    CU(cudaEventRecord(s.ev_begin, e->stream));
+
+    /* 1. move new bytes to HBM and decide how many frames and batches every input runs */
+    std::vector<size_t> ring_taken(nd, 0);
+    bool any_ring = false;
+    for (size_t di = 0; di < nd; di++) {
+        Dev& d = *e->dev[di];
+        const uint64_t room = frame_room(e, d);
+        uint64_t total = 0;
+        if (d.injected) {
+            total = 0; /* frames arrive through ba_cuda_debug_inject_picks() */
+        } else if (d.attached) {
+            total = d.attached_valid;
+        } else {
+            std::lock_guard<std::mutex> g(d.lock);
+            const uint64_t next_off = d.frames_done * d.hop_bytes; /* stream offset of the next frame */
+            const size_t lo = (size_t)(next_off - d.base_off);
+            const size_t carry = d.have - lo;
+            /* most bytes this step can use: enough for `room` frames under the availability rule */
+            const uint64_t want_total = next_off + room * d.hop_bytes + d.frame_bytes + d.hop_bytes;
+            const uint64_t have_total = d.base_off + d.have;
+            size_t take_ring = 0;
+            std::vector<ExtChunk> take_ext;
+            if (have_total < want_total) {
+                uint64_t want = want_total - have_total;
+                const size_t cap_left = d.d_cap - carry;
+                if (want > cap_left)
+                    want = cap_left;
+                take_ring = (size_t)std::min<uint64_t>(ring_available(d), want);
+                want -= take_ring;
+                while (want > 0 && !d.ext.empty()) {
+                    ExtChunk& c = d.ext.front();
+                    const size_t n = (size_t)std::min<uint64_t>(c.n, want);
+                    take_ext.push_back(ExtChunk{c.p, n});
+                    c.p += n;
+                    c.n -= n;
+                    want -= n;
+                    if (c.n == 0)
+                        d.ext.erase(d.ext.begin());
+                }
+            }
+            if (take_ring || !take_ext.empty()) {
+                const int nxt = d.cur ^ 1;
+                if (carry)
+                    CU(cudaMemcpyAsync(d.d_buf[nxt], d.d_buf[d.cur] + lo, carry, cudaMemcpyDeviceToDevice, e->stream));
+                size_t at = carry;
+                if (take_ring) {
+                    const size_t first = std::min(take_ring, d.buf_size - d.bufs);
+                    CU(cudaMemcpyAsync(d.d_buf[nxt] + at, d.ring + d.bufs, first, cudaMemcpyHostToDevice, e->stream));
+                    if (take_ring > first)
+                        CU(cudaMemcpyAsync(d.d_buf[nxt] + at + first, d.ring, take_ring - first, cudaMemcpyHostToDevice, e->stream));
+                    at += take_ring;
+                    s.h2d_bytes += take_ring;
+                    ring_taken[di] = take_ring;
+                    any_ring = true;
+                }
+                for (const ExtChunk& c : take_ext) {
+                    CU(cudaMemcpyAsync(d.d_buf[nxt] + at, c.p, c.n, cudaMemcpyHostToDevice, e->stream));
+                    at += c.n;
+                    s.h2d_bytes += c.n;
+                }
+                d.cur = nxt;
+                d.base_off = next_off;
+                d.have = at;
+            }
+            total = d.base_off + d.have;
+        }
+        uint64_t nf = frames_admitted(d, total);
+        nf = nf > d.frames_done ? nf - d.frames_done : 0;
+        if (nf > room)
+            nf = room;
+        d.step_frame0 = d.frames_done;
+        d.step_frames = (int)nf;
+        const uint64_t after = d.frames_done + nf;
+        uint64_t nb = after >= (uint64_t)BA_E ? (after - BA_E) / B : 0;
+        nb = nb > d.batches_done ? nb - d.batches_done : 0;
+        if (nb > (uint64_t)e->max_batches)
+            nb = e->max_batches;
+        d.step_batch0 = d.batches_done;
+        d.step_batches = (int)nb;
+    }
+    if (any_ring) {
+        /* the pinned rings are read by the copy engine: give the bytes back to the producers (bufs, .cpp:735) only once the copies are done */
+        CU(cudaStreamSynchronize(e->stream));
+        for (size_t di = 0; di < nd; di++)
+            if (ring_taken[di]) {
+                Dev& d = *e->dev[di];
+                std::lock_guard<std::mutex> g(d.lock);
+                d.bufs = (d.bufs + ring_taken[di]) % d.buf_size;
+            }
+    }
+
+    /* 2. phases: one for ordinary inputs; an AFC input alternates K1/K2 per batch */
+    int phases = 1;
+    for (Dev* d : e->dev)
+        if (d->any_afc)
+            phases = std::max(phases, d->step_batches + 1);
+    K1Device* h_k1 = reinterpret_cast<K1Device*>(s.h_desc);
+    K2Dyn* h_dyn = reinterpret_cast<K2Dyn*>(s.h_desc + (size_t)e->max_phases * nd * sizeof(K1Device));
+    K1Device* d_k1 = reinterpret_cast<K1Device*>(s.d_desc);
+    K2Dyn* d_dyn = reinterpret_cast<K2Dyn*>(s.d_desc + (size_t)e->max_phases * nd * sizeof(K1Device));
+    std::vector<int> k1_count(phases, 0), k1_tiles(phases, 0), k2_any(phases, 0);
+    for (int ph = 0; ph < phases; ph++) {
+        for (size_t di = 0; di < nd; di++) {
+            Dev& d = *e->dev[di];
+            uint64_t f_begin, f_end;
+            int nb_here, b_first;
+            if (!d.any_afc) {
+                f_begin = d.step_frame0;
+                f_end = ph == 0 ? d.step_frame0 + d.step_frames : f_begin;
+                nb_here = ph == 0 ? d.step_batches : 0;
+                b_first = 0;
+            } else {
+                const uint64_t step_end = d.step_frame0 + d.step_frames;
+                auto batch_end = [&](int i) { return std::min<uint64_t>(step_end, (d.step_batch0 + i + 1) * (uint64_t)B + BA_E); };
+                f_begin = ph == 0 ? d.step_frame0 : std::max<uint64_t>(d.step_frame0, batch_end(ph - 1));
+                if (ph < d.step_batches) {
+                    f_end = batch_end(ph);
+                    nb_here = 1;
+                } else {
+                    f_end = ph == d.step_batches ? step_end : f_begin;
+                    nb_here = 0;
+                }
+                if (f_end < f_begin)
+                    f_end = f_begin;
+                b_first = ph;
+            }
+            if (f_end > f_begin) {
+                K1Device& k = h_k1[(size_t)ph * nd + k1_count[ph]];
+                memset(&k, 0, sizeof(k));
+                const uint64_t off = f_begin * d.hop_bytes;
+                if (d.attached) {
+                    k.iq = d.attached + off;
+                    k.lo = d.attached;
+                    k.hi = d.attached + d.attached_valid;
+                } else {
+                    k.iq = d.d_buf[d.cur] + (size_t)(off - d.base_off);
+                    k.lo = d.d_buf[d.cur];
+                    k.hi = d.d_buf[d.cur] + d.have;
+                }
+                k.hop_bytes = (uint32_t)d.hop_bytes;
+                k.n_frames = (uint32_t)(f_end - f_begin);
+                k.frame0 = f_begin;
+                k.picks = d.d_picks;
+                k.ring_mask = d.ring_len - 1;
+                k.c_pad = (uint32_t)d.c_pad;
+                k.n_channels = (uint32_t)d.C;
+                k.tile0 = (uint32_t)k1_tiles[ph];
+                k.bins = d.d_bins;
+                k.scale = 1.0f / d.cfg.fullscale;
+                k.fmt = d.cfg.sample_format;
+                k.spectrum = (d.any_afc && nb_here) ? d.d_spectrum : nullptr;
+                k1_tiles[ph] += (int)((k.n_frames + e->tile_frames - 1) / e->tile_frames);
+                k1_count[ph]++;
+            }
+            K2Dyn& y = h_dyn[(size_t)ph * nd + di];
+            memset(&y, 0, sizeof(y));
+            y.n_batches = nb_here;
+            if (nb_here) {
+                k2_any[ph] = 1;
+                const size_t shift = (size_t)b_first * B;
+                y.first_frame = (d.step_batch0 + b_first) * (uint64_t)B + BA_E;
+                y.stride = (uint32_t)e->stride;
+                y.n_channels = (uint32_t)d.C;
+                y.waveout = s.d_wave + d.wave_off + shift;
+                y.iq_out = (s.d_iq && d.any_iq) ? s.d_iq + d.iq_off + shift : nullptr;
+                y.trace = s.d_trace ? s.d_trace + d.wave_off + shift : nullptr;
+                y.status = s.d_status + d.status_off + (size_t)b_first * d.C;
+                y.spectrum = d.any_afc ? d.d_spectrum : nullptr;
+            }
+        }
+    }
+    CU(cudaMemcpyAsync(s.d_desc, s.h_desc, e->desc_bytes, cudaMemcpyHostToDevice, e->stream));
+
+    /* 3. launches */
+    for (int ph = 0; ph < phases; ph++) {
+        CU(cudaEventRecord(s.ev_k[3 * ph + 0], e->stream));
+        if (k1_count[ph]) {
+            K1Params p;
+            p.dev = d_k1 + (size_t)ph * nd;
+            p.n_dev = k1_count[ph];
+            p.tile_frames = e->tile_frames;
+            p.n_tiles = k1_tiles[ph];
+            p.window = e->d_window;
+            p.twiddle = e->d_twiddle;
+            p.raw_bytes = e->raw_bytes;
+            p.max_channels = e->max_channels;
+            const int ctas = std::min(p.n_tiles, e->sm_count * e->k1_ctas_per_sm);
+            int rc = k1_launch(e->fft_size, p, ctas, e->stream);
+            if (rc != 0)
+                return fail(BA_ERR_CUDA, "channelize launch: %s", cudaGetErrorString((cudaError_t)rc));
+            e->launches++;
+        }
+        CU(cudaEventRecord(s.ev_k[3 * ph + 1], e->stream));
+        if (k2_any[ph]) {
+            K2Params p;
+            p.chan = e->d_chan;
+            p.state = e->d_state;
+            p.dyn = d_dyn + (size_t)ph * nd;
+            p.order = e->d_order;
+            p.n_channels = e->total_channels;
+            p.wave_batch = B;
+            p.sincos = e->d_sincos;
+            int rc = k2_launch(p, e->stream);
+            if (rc != 0)
+                return fail(BA_ERR_CUDA, "demod launch: %s", cudaGetErrorString((cudaError_t)rc));
+            e->launches++;
+        }
+        CU(cudaEventRecord(s.ev_k[3 * ph + 2], e->stream));
+    }
+    s.phases = phases;
+
+    /* 4. results to pinned host memory */
+    {
+        bool uniform = true;
+        int nb0 = e->dev[0]->step_batches;
+        for (Dev* d : e->dev)
+            uniform = uniform && d->step_batches == nb0;
+        auto copy_rows = [&](size_t off, size_t rows, int nb) -> int {
+            const size_t width = (size_t)nb * B;
+            CU(cudaMemcpy2DAsync(s.h_wave + off, sizeof(float) * e->stride, s.d_wave + off, sizeof(float) * e->stride, sizeof(float) * width, rows, cudaMemcpyDeviceToHost,
+                                 e->stream));
+            s.d2h_bytes += sizeof(float) * width * rows;
+            if (s.d_trace) {
+                CU(cudaMemcpy2DAsync(s.h_trace + off, e->stride, s.d_trace + off, e->stride, width, rows, cudaMemcpyDeviceToHost, e->stream));
+                s.d2h_bytes += width * rows;
+            }
+            return BA_OK;
+        };
+        if (uniform) {
+            if (nb0 > 0) {
+                int rc = copy_rows(0, (size_t)e->total_channels, nb0);
+                if (rc != BA_OK)
+                    return rc;
+            }
+        } else {
+            for (Dev* d : e->dev)
+                if (d->step_batches > 0) {
+                    int rc = copy_rows(d->wave_off, (size_t)d->C, d->step_batches);
+                    if (rc != BA_OK)
+                        return rc;
+                }
+        }
+        for (Dev* d : e->dev) {
+            if (d->step_batches <= 0)
+                continue;
+            if (s.d_iq && d->any_iq) {
+                const size_t width = (size_t)d->step_batches * B;
+                CU(cudaMemcpy2DAsync(s.h_iq + d->iq_off, sizeof(float2) * e->stride, s.d_iq + d->iq_off, sizeof(float2) * e->stride, sizeof(float2) * width, (size_t)d->C,
+                                     cudaMemcpyDeviceToHost, e->stream));
+                s.d2h_bytes += sizeof(float2) * width * d->C;
+            }
+        }
+        bool any = false;
+        for (Dev* d : e->dev)
+            any = any || d->step_batches > 0;
+        if (any) {
+            size_t total_status = 0;
+            for (Dev* d : e->dev)
+                total_status += (size_t)d->C * e->max_batches;
+            CU(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(ba_channel_status) * total_status, cudaMemcpyDeviceToHost, e->stream));
+            s.d2h_bytes += sizeof(ba_channel_status) * total_status;
+        }
+    }
+    CU(cudaEventRecord(s.ev_done, e->stream));
+
+    for (size_t di = 0; di < nd; di++) {
+        Dev& d = *e->dev[di];
+        d.frames_done += (uint64_t)d.step_frames;
+        d.batches_done += (uint64_t)d.step_batches;
+        s.n_batches[di] = d.step_batches;
+        s.frames_done[di] = d.frames_done;
+    }
+    s.ticket = ticket;
+    s.busy = true;
+    e->next_ticket++;
+    return ticket;
+}
+
+static Slot* find_slot(ba_engine* e, int ticket) {
+    if (!e || ticket < 0) {
+        fail(BA_ERR_BAD_ARG, "bad ticket %d", ticket);
+        return nullptr;
+    }
+    Slot& s = e->slot[ticket & 1];
+    if (s.ticket != ticket) {
+        fail(BA_ERR_STATE, "ticket %d is not outstanding (slot holds %d)", ticket, s.ticket);
+        return nullptr;
+    }
+    return &s;
+}
+
+int ba_cuda_collect(ba_engine* e, int ticket, int dev, ba_step_out* out) {
+    Slot* s = find_slot(e, ticket);
+    Dev* d = get_dev(e, dev);
+    if (!s || !d || !out)
+        return s && d ? fail(BA_ERR_BAD_ARG, "null out") : BA_ERR_BAD_ARG;
+    CU(cudaEventSynchronize(s->ev_done));
+    s->busy = false;
+    memset(out, 0, sizeof(*out));
+    out->n_batches = s->n_batches[dev];
+    out->wave_batch = e->B;
+    out->channel_count = d->C;
+    out->wave_stride = e->stride;
+    out->waveout = s->h_wave + d->wave_off;
+    out->iq_out = (s->h_iq && d->any_iq) ? reinterpret_cast<const float*>(s->h_iq + d->iq_off) : nullptr;
+    out->trace = s->h_trace ? s->h_trace + d->wave_off : nullptr;
+    out->status = s->h_status + d->status_off;
+    out->frames_done = s->frames_done[dev];
+    return BA_OK;
+}
+
+int ba_cuda_ticket_ms(ba_engine* e, int ticket, float* ms) {
+    Slot* s = find_slot(e, ticket);
+    if (!s || !ms)
+        return BA_ERR_BAD_ARG;
+    CU(cudaEventSynchronize(s->ev_done));
+    CU(cudaEventElapsedTime(ms, s->ev_begin, s->ev_done));
+    return BA_OK;
+}
+
+int ba_cuda_kernel_ms(ba_engine* e, int ticket, float ms[2]) {
+    Slot* s = find_slot(e, ticket);
+    if (!s || !ms)
+        return BA_ERR_BAD_ARG;
+    CU(cudaEventSynchronize(s->ev_done));
+    ms[0] = ms[1] = 0.0f;
+    for (int ph = 0; ph < s->phases; ph++) {
+        float a = 0, b = 0;
+        CU(cudaEventElapsedTime(&a, s->ev_k[3 * ph + 0], s->ev_k[3 * ph + 1]));
+        CU(cudaEventElapsedTime(&b, s->ev_k[3 * ph + 1], s->ev_k[3 * ph + 2]));
+        ms[0] += a;
+        ms[1] += b;
+    }
+    return BA_OK;
+}
+
+int ba_cuda_step_bytes(ba_engine* e, int ticket, uint64_t* h2d, uint64_t* d2h) {
+    Slot* s = find_slot(e, ticket);
+    if (!s)
+        return BA_ERR_BAD_ARG;
+    if (h2d)
+        *h2d = s->h2d_bytes;
+    if (d2h)
+        *d2h = s->d2h_bytes;
+    return BA_OK;
+}
+
+int ba_cuda_channel_info(ba_engine* e, int dev, int channel, ba_channel_info* out) {
+    Dev* d = get_dev(e, dev);
+    if (!d || !out || channel < 0 || channel >= d->C)
+        return fail(BA_ERR_BAD_ARG, "bad argument");
+    *out = e->info[d->first_chan + channel];
+    return BA_OK;
+}
+
+int ba_cuda_window(ba_engine* e, float* out, size_t count) {
+    if (!e || !out || count != e->window.size())
+        return fail(BA_ERR_BAD_ARG, "bad argument");
+    memcpy(out, e->window.data(), count * sizeof(float));
+    return BA_OK;
+}
+
+int ba_cuda_launch_count(ba_engine* e, uint64_t* launches) {
+    if (!e || !launches)
+        return fail(BA_ERR_BAD_ARG, "bad argument");
+    *launches = e->launches;
+    return BA_OK;
+}
+
+int ba_cuda_debug_frames(ba_engine* e, int dev, const void* iq, size_t bytes, int n_frames, float* fftin, float* fftout) {
+    using namespace ba;
+    Dev* d = get_dev(e, dev);
+    if (!d || !iq || n_frames <= 0)
+        return fail(BA_ERR_BAD_ARG, "bad argument");
+    const size_t N = (size_t)e->fft_size;
+    if ((size_t)(n_frames - 1) * d->hop_bytes + d->frame_bytes > bytes)
+        return fail(BA_ERR_BAD_ARG, "%d frames need %zu bytes, %zu given", n_frames, (size_t)(n_frames - 1) * d->hop_bytes + d->frame_bytes, bytes);
+    unsigned char* d_iq = nullptr;
+    float2 *d_in = nullptr, *d_out = nullptr, *d_picks = nullptr;
+    K1Device* d_k = nullptr;
+    const uint32_t ring_len = pow2_at_least((uint64_t)n_frames);
+    int rc = BA_OK;
+    auto cleanup = [&]() {
+        cudaFree(d_iq);
+        cudaFree(d_in);
+        cudaFree(d_out);
+        cudaFree(d_picks);
+        cudaFree(d_k);
+    };
+#define CUD(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (cudaError_t)(call);                                                      \
+        if (e_ != cudaSuccess) {                                                                   \
+            cleanup();                                                                             \
+            return fail(BA_ERR_CUDA, "%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                          \
+    } while (0)
+    CUD(cudaStreamSynchronize(e->stream));
+    CUD(cudaMalloc((void**)&d_iq, bytes + 1));
+    CUD(cudaMalloc((void**)&d_in, sizeof(float2) * N * n_frames));
+    CUD(cudaMalloc((void**)&d_out, sizeof(float2) * N * n_frames));
+    CUD(cudaMalloc((void**)&d_picks, sizeof(float2) * (size_t)ring_len * d->c_pad));
+    CUD(cudaMalloc((void**)&d_k, sizeof(K1Device)));
+    CUD(cudaMemcpy(d_iq, iq, bytes, cudaMemcpyHostToDevice));
+    K1Device k;
+    memset(&k, 0, sizeof(k));
+    k.iq = d_iq;
+    k.lo = d_iq;
+    k.hi = d_iq + bytes;
+    k.hop_bytes = (uint32_t)d->hop_bytes;
+    k.n_frames = (uint32_t)n_frames;
+    k.frame0 = 0;
+    k.picks = d_picks;
+    k.ring_mask = ring_len - 1;
+    k.c_pad = (uint32_t)d->c_pad;
+    k.n_channels = (uint32_t)d->C;
+    k.tile0 = 0;
+    k.bins = d->d_bins;
+    k.scale = 1.0f / d->cfg.fullscale;
+    k.fmt = d->cfg.sample_format;
+    k.dbg_in = fftin ? d_in : nullptr;
+    k.dbg_out = fftout ? d_out : nullptr;
+    CUD(cudaMemcpy(d_k, &k, sizeof(k), cudaMemcpyHostToDevice));
+    K1Params p;
+    p.dev = d_k;
+    p.n_dev = 1;
+    p.tile_frames = e->tile_frames;
+    p.n_tiles = (n_frames + e->tile_frames - 1) / e->tile_frames;
+    p.window = e->d_window;
+    p.twiddle = e->d_twiddle;
+    p.raw_bytes = e->raw_bytes;
+    p.max_channels = e->max_channels;
+    rc = k1_launch(e->fft_size, p, std::min(p.n_tiles, e->sm_count), e->stream);
+    if (rc != 0) {
+        cleanup();
+        return fail(BA_ERR_CUDA, "channelize launch: %s", cudaGetErrorString((cudaError_t)rc));
+    }
+    e->launches++;
+    CUD(cudaStreamSynchronize(e->stream));
+    if (fftin)
+        CUD(cudaMemcpy(fftin, d_in, sizeof(float2) * N * n_frames, cudaMemcpyDeviceToHost));
+    if (fftout)
+        CUD(cudaMemcpy(fftout, d_out, sizeof(float2) * N * n_frames, cudaMemcpyDeviceToHost));
+#undef CUD
+    cleanup();
+    return BA_OK;
+}
+
+int ba_cuda_debug_picks(ba_engine* e, int dev, int channel, uint64_t first, int count, float* out) {
+    Dev* d = get_dev(e, dev);
+    if (!d || !out || channel < 0 || channel >= d->C || count < 0)
+        return fail(BA_ERR_BAD_ARG, "bad argument");
+    if (first + (uint64_t)count > d->frames_done || d->frames_done - first > d->ring_len)
+        return fail(BA_ERR_BAD_ARG, "frames [%llu, +%d) are not in the pick ring (frames done %llu, ring %u)", (unsigned long long)first, count,
+                    (unsigned long long)d->frames_done, d->ring_len);
+    CU(cudaStreamSynchronize(e->stream));
+    uint64_t f = first;
+    int left = count;
+    while (left > 0) {
+        const uint32_t pos = (uint32_t)(f & (d->ring_len - 1));
+        const int n = (int)std::min<uint64_t>((uint64_t)left, d->ring_len - pos);
+        CU(cudaMemcpy2D(out + 2 * (f - first), sizeof(float2), d->d_picks + (size_t)pos * d->c_pad + channel, sizeof(float2) * d->c_pad, sizeof(float2), (size_t)n,
+                        cudaMemcpyDeviceToHost));
+        f += n;
+        left -= n;
+    }
+    return BA_OK;
+}
+
+int ba_cuda_debug_inject_picks(ba_engine* e, int dev, const float* picks, int n_frames) {
+    Dev* d = get_dev(e, dev);
+    if (!d || !picks || n_frames < 0)
+        return fail(BA_ERR_BAD_ARG, "bad argument");
+    if ((uint64_t)n_frames > frame_room(e, *d))
+        return fail(BA_ERR_OVERRUN, "input %d: room for %llu more frames before the next ba_cuda_process()", dev, (unsigned long long)frame_room(e, *d));
+    CU(cudaStreamSynchronize(e->stream));
+    uint64_t f = d->frames_done;
+    int left = n_frames;
+    const float* src = picks;
+    while (left > 0) {
+        const uint32_t pos = (uint32_t)(f & (d->ring_len - 1));
+        const int n = (int)std::min<uint64_t>((uint64_t)left, d->ring_len - pos);
+        CU(cudaMemcpy2D(d->d_picks + (size_t)pos * d->c_pad, sizeof(float2) * d->c_pad, src, sizeof(float2) * d->C, sizeof(float2) * d->C, (size_t)n, cudaMemcpyHostToDevice));
+        src += 2 * (size_t)n * d->C;
+        f += n;
+        left -= n;
+    }
+    d->frames_done = f;
+    d->injected = true;
+    return BA_OK;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,147 @@
+/*
+ * ba_kernels.h — device-side job descriptors shared by the host engine (ba_engine.cu) and the two kernels:
+ *   K1  channelize  (channelize.cu)  expand + window + batched in-shared-memory FFT + per-channel bin pick
+ *                                     replaces boondock_airband.cpp:426-516 (and hello_fft + samplefft on the Pi)
+ *   K2  demod       (demod.cu)       the per-channel sample loop, boondock_airband.cpp:518-679, with Squelch,
+ *                                     CTCSS, NotchFilter, LowpassFilter state resident in HBM between launches
+ */
+#ifndef BA_KERNELS_H
+#define BA_KERNELS_H
+
+#include <stdint.h>
+
+#include "../../include/ba_cuda.h"
+#include "ba_port.h"
+
+#define BA_E 100       /* AGC_EXTRA, boondock_airband.h:74 */
+#define BA_SQ_RING 102 /* Squelch::buffer_size_, squelch.cpp:67 */
+#define BA_MAX_TONES 52 /* 1 target + 51 standard tones, ctcss.cpp:101-118 */
+
+namespace ba {
+
+/* ------------------------------------------------------------------ K1 */
+
+/* one input (device_t) as K1 sees it for one launch */
+struct K1Device {
+    const unsigned char* iq; /* first byte of frame 0 of this launch (device memory) */
+    const unsigned char* lo; /* [lo, hi): bytes that may be touched by 16-byte vector loads */
+    const unsigned char* hi;
+    uint32_t hop_bytes;      /* bps, boondock_airband.cpp:418 */
+    uint32_t n_frames;       /* frames in this launch */
+    uint64_t frame0;         /* stream index of frame 0 */
+    float2* picks;           /* [ring_len][c_pad]: fftout[bins[c]] per frame, ring over frames */
+    uint32_t ring_mask;      /* ring_len - 1 */
+    uint32_t c_pad;
+    uint32_t n_channels;
+    uint32_t tile0;          /* first tile index of this device in the launch-wide tile list */
+    const uint32_t* bins;    /* device-resident dev->bins[] (AFC may move them between launches) */
+    float scale;             /* 1 / fullscale (S16, F32) */
+    int32_t fmt;             /* BA_SFMT_* */
+    float2* spectrum;        /* AFC: full spectrum of the last frame of the launch (natural bin order) or NULL */
+    float2* dbg_in;          /* tests: converted frames [n_frames][N] or NULL */
+    float2* dbg_out;         /* tests: spectra [n_frames][N], natural order, or NULL */
+};
+
+struct K1Params {
+    const K1Device* dev;
+    int32_t n_dev;
+    int32_t tile_frames;   /* frames per tile */
+    int32_t n_tiles;       /* total tiles over all devices */
+    const float* window;   /* [N], boondock_airband.cpp:357-373 */
+    const float2* twiddle; /* [N], exp(-2 pi i n / N), rounded from double */
+    int32_t raw_bytes;     /* shared-memory bytes reserved for the staged byte span of one tile (multiple of 16) */
+    int32_t max_channels;  /* largest channel_count of any input (pick table size) */
+};
+
+/* returns 0 or a cudaError_t */
+int k1_launch(int fft_size, const K1Params& p, int n_ctas, cudaStream_t s);
+int k1_smem_bytes(int fft_size, int raw_bytes, int max_channels);
+int k1_threads(int fft_size);
+int k1_groups(int fft_size); /* FFTs a CTA works on at a time */
+
+/* ------------------------------------------------------------------ K2 */
+
+/* Goertzel bank pair of one CTCSS channel: constants and resident state (ctcss.cpp) */
+struct K2Ctcss {
+    int32_t n_fast, n_slow, win_fast, win_slow;
+    float coeff_fast[BA_MAX_TONES], coeff_slow[BA_MAX_TONES];
+    /* state */
+    int32_t fast_full, fast_fed, fast_tone, slow_full, slow_fed, slow_tone;
+    uint32_t slow_hits, slow_misses;
+    float fq1[BA_MAX_TONES], fq2[BA_MAX_TONES], sq1[BA_MAX_TONES], sq2[BA_MAX_TONES];
+};
+
+/* constants of one channel (channel_t + freq_t + its Squelch/filter configuration) */
+struct K2Chan {
+    int32_t dev;          /* input index (K2Dyn) */
+    uint32_t col;         /* channel index within its input = column of the pick row */
+    const float2* picks;  /* its input's pick ring */
+    uint32_t ring_mask, c_pad;
+    uint32_t* bin;        /* &bins[col] (AFC moves it) */
+    uint32_t base_bin;
+    int32_t fft_size;
+    /* channel_t / freq_t */
+    int32_t modulation, afc, needs_raw_iq, has_iq_outputs, fm_demod;
+    uint32_t dm_dphi;
+    float alpha, ampfactor;
+    /* Squelch configuration (squelch.cpp:36-116) */
+    int32_t manual;
+    float manual_level, ratio, flappy_ratio;
+    /* filters (filters.cpp) */
+    int32_t notch_on, lp_on;
+    float nd0, nd1, nd2;
+    float lp_gain, lp_c0, lp_c1;
+    /* CTCSS */
+    K2Ctcss* ctcss; /* NULL when the channel has no ctcss */
+};
+
+/* mutable state of one channel, resident in HBM between launches */
+struct K2State {
+    /* Squelch */
+    float noise, cap, pre_full, pre_cap, post_full, post_cap;
+    int32_t post_active, next, cur, delay, low_run;
+    uint32_t opens, flappy, recent_opens, closed_run, count16;
+    int32_t head, tail;
+    /* channel */
+    uint32_t dm_phi;
+    float pr, pj, prev_waveout, agcavgfast;
+    uint32_t active_counter;
+    int32_t axcindicate;
+    int32_t hist_ready; /* 0 until the first launch has seeded wavein_hist from frames 0..E-1 */
+    int32_t hist_pos;   /* slot of wavein_hist the next sample uses (frame index mod E) */
+    /* filters */
+    float nx0, nx1, nx2, ny0, ny1, ny2;
+    float lxr0, lxr1, lxr2, lxi0, lxi1, lxi2, lyr0, lyr1, lyr2, lyi0, lyi1, lyi2;
+    float ring[BA_SQ_RING];    /* Squelch::buffer_ */
+    float wavein_hist[BA_E];   /* wavein[] as the loop left it for the last E frames (.cpp:548 overwrites it) */
+    float waveout_tail[BA_E];  /* waveout[B..B+E) kept by output_thread for the next batch (output.cpp:948) */
+};
+
+/* per input, per launch */
+struct K2Dyn {
+    uint64_t first_frame; /* stream index of the first frame the squelch sees: batches_done*B + E */
+    int32_t n_batches;    /* batches of this input in this launch (0 = nothing to do) */
+    uint32_t stride;      /* elements between consecutive channels in waveout / iq_out / trace */
+    uint32_t n_channels;  /* channels of this input (row length of status) */
+    uint32_t pad0;
+    float* waveout;       /* [C][stride]; row positions [0,E) hold the tail carried in, [0, n_batches*B) go to the host */
+    float2* iq_out;       /* [C][stride] or NULL */
+    uint8_t* trace;       /* [C][stride] or NULL */
+    ba_channel_status* status; /* [max_batches][C] */
+    const float2* spectrum;    /* AFC: spectrum of the last frame K1 produced (the last frame of the batch) or NULL */
+};
+
+struct K2Params {
+    const K2Chan* chan;
+    K2State* state;
+    const K2Dyn* dyn;     /* [n inputs] */
+    const int32_t* order; /* channel indices in launch order (grouped by kind so that warps stay convergent) */
+    int32_t n_channels;
+    int32_t wave_batch;   /* B */
+    const float* sincos;  /* [2][257] sin then cos, util.cpp:103-110 */
+};
+
+int k2_launch(const K2Params& p, cudaStream_t s);
+
+}  // namespace ba
+#endif

@@ -1,0 +1,273 @@
+"""Python host side of the engine: a thin ctypes binding of the C-ABI in include/ba_cuda.h.
+
+``Engine`` plays the part of one ``demodulate()`` thread of the reference (boondock_airband.cpp:308-738) for the
+devices in its ``EngineCfg``: input bytes go in with ``submit`` (the ``circbuffer_append`` of input-helpers.cpp:37-63),
+``process`` runs one pass of the hot path over everything that is waiting, ``collect`` hands back what the reference
+hands to its output thread after each batch (waveout, iq_out, axcindicate and the squelch levels).
+
+All computation happens in libba_cuda.so (hand-written sm_100a kernels).  There is no fallback: if the library is
+missing or no CUDA device is visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional
+
+import numpy as np
+
+from . import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libba_cuda.so")
+
+_LIBS = {}
+
+# every symbol include/ba_cuda.h declares
+SYMBOLS = (
+    "ba_cuda_create", "ba_cuda_destroy", "ba_cuda_last_error", "ba_cuda_visible_devices", "ba_cuda_input_ring",
+    "ba_cuda_submit", "ba_cuda_commit", "ba_cuda_submit_external", "ba_cuda_attach_device_stream",
+    "ba_cuda_advance_device_stream", "ba_cuda_process", "ba_cuda_collect", "ba_cuda_ticket_ms", "ba_cuda_step_bytes",
+    "ba_cuda_channel_info", "ba_cuda_window", "ba_cuda_debug_frames", "ba_cuda_debug_picks",
+    "ba_cuda_debug_inject_picks", "ba_cuda_launch_count", "ba_cuda_kernel_ms",
+)
+
+
+class EngineError(RuntimeError):
+    def __init__(self, where: str, code: int, text: str):
+        super().__init__("%s: %s (%d) %s" % (where, abi.ERRORS.get(code, "?"), code, text))
+        self.code = code
+
+
+def load_library(path: Optional[str] = None):
+    path = path or LIB_PATH
+    if path in _LIBS:
+        return _LIBS[path]
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            path + " is missing: build it with `make -C boondock_airband_b200/csrc` (or __graft_entry__.build()); "
+            "there is no CPU implementation to fall back to")
+    L = C.CDLL(path)
+    vp, sz, u64p = C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)
+    L.ba_cuda_create.argtypes = [C.POINTER(abi.EngineDesc), C.POINTER(vp)]
+    L.ba_cuda_destroy.argtypes = [vp]
+    L.ba_cuda_destroy.restype = None
+    L.ba_cuda_last_error.restype = C.c_char_p
+    L.ba_cuda_visible_devices.argtypes = []
+    L.ba_cuda_input_ring.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
+    L.ba_cuda_submit.argtypes = [vp, C.c_int, vp, sz]
+    L.ba_cuda_commit.argtypes = [vp, C.c_int, sz]
+    L.ba_cuda_submit_external.argtypes = [vp, C.c_int, vp, sz]
+    L.ba_cuda_attach_device_stream.argtypes = [vp, C.c_int, vp, sz]
+    L.ba_cuda_advance_device_stream.argtypes = [vp, C.c_int, sz]
+    L.ba_cuda_process.argtypes = [vp]
+    L.ba_cuda_collect.argtypes = [vp, C.c_int, C.c_int, C.POINTER(abi.StepOut)]
+    L.ba_cuda_ticket_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+    L.ba_cuda_step_bytes.argtypes = [vp, C.c_int, u64p, u64p]
+    L.ba_cuda_channel_info.argtypes = [vp, C.c_int, C.c_int, C.POINTER(abi.ChannelInfo)]
+    L.ba_cuda_window.argtypes = [vp, C.POINTER(C.c_float), sz]
+    L.ba_cuda_debug_frames.argtypes = [vp, C.c_int, vp, sz, C.c_int, vp, vp]
+    L.ba_cuda_debug_picks.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, C.c_int, vp]
+    L.ba_cuda_debug_inject_picks.argtypes = [vp, C.c_int, vp, C.c_int]
+    L.ba_cuda_launch_count.argtypes = [vp, u64p]
+    L.ba_cuda_kernel_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+    _LIBS[path] = L
+    return L
+
+
+class StepResult:
+    """What one ``process()`` produced for one device (views into pinned host memory, copied on access)."""
+
+    def __init__(self, out: abi.StepOut):
+        self.n_batches = out.n_batches
+        self.wave_batch = out.wave_batch
+        self.channel_count = out.channel_count
+        self.frames_done = out.frames_done
+        n = self.n_batches * self.wave_batch
+        c, stride = self.channel_count, out.wave_stride
+        if n > 0:
+            full = np.ctypeslib.as_array(out.waveout, shape=(c, stride))
+            self.waveout = full[:, :n].copy()
+            self.iq_out = None
+            if out.iq_out:
+                iq = np.ctypeslib.as_array(out.iq_out, shape=(c, stride, 2))
+                self.iq_out = iq[:, :n, :].copy()
+            self.trace = None
+            if out.trace:
+                tr = np.ctypeslib.as_array(out.trace, shape=(c, stride))
+                self.trace = tr[:, :n].copy()
+            st = np.ctypeslib.as_array(C.cast(out.status, C.POINTER(C.c_uint32)), shape=(self.n_batches, c, 10)).copy()
+            self.status_raw = st
+        else:
+            self.waveout = np.zeros((c, 0), np.float32)
+            self.iq_out = None
+            self.trace = None
+            self.status_raw = np.zeros((0, c, 10), np.uint32)
+
+    def status(self, batch: int, channel: int) -> dict:
+        r = self.status_raw[batch, channel]
+        f = r.view(np.float32)
+        return dict(axcindicate=int(r[0].view(np.int32)), bin=int(r[1]), signal_level=float(f[2]), noise_level=float(f[3]),
+                    squelch_level=float(f[4]), open_count=int(r[5]), flappy_count=int(r[6]), ctcss_count=int(r[7]),
+                    no_ctcss_count=int(r[8]), active_counter=int(r[9]))
+
+
+class Engine:
+    def __init__(self, cfg: abi.EngineCfg, lib_path: Optional[str] = None):
+        self.cfg = cfg
+        self.L = load_library(lib_path)
+        desc, self._keep = abi.build_desc(cfg)
+        h = C.c_void_p()
+        rc = self.L.ba_cuda_create(C.byref(desc), C.byref(h))
+        if rc != 0:
+            raise EngineError("ba_cuda_create", rc, self.L.ba_cuda_last_error().decode())
+        self.h = h
+        self._pins: List[object] = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ba_cuda_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, where: str, rc: int) -> int:
+        if rc < 0:
+            raise EngineError(where, rc, self.L.ba_cuda_last_error().decode())
+        return rc
+
+    # ---- input side
+    def submit(self, dev: int, iq: np.ndarray):
+        """Append interleaved IQ to the device's pinned ring (circbuffer_append, input-helpers.cpp:37-63)."""
+        iq = np.ascontiguousarray(iq)
+        self._check("ba_cuda_submit", self.L.ba_cuda_submit(self.h, dev, iq.ctypes.data, iq.nbytes))
+
+    def submit_external(self, dev: int, ptr: int, nbytes: int, keepalive=None):
+        if keepalive is not None:
+            self._pins.append(keepalive)
+        self._check("ba_cuda_submit_external", self.L.ba_cuda_submit_external(self.h, dev, ptr, nbytes))
+
+    def input_ring(self, dev: int):
+        buf, size, mirror = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        self._check("ba_cuda_input_ring", self.L.ba_cuda_input_ring(self.h, dev, C.byref(buf), C.byref(size), C.byref(mirror)))
+        return buf.value, size.value, mirror.value
+
+    def commit(self, dev: int, nbytes: int):
+        self._check("ba_cuda_commit", self.L.ba_cuda_commit(self.h, dev, nbytes))
+
+    def attach_device_stream(self, dev: int, device_ptr: int, capacity: int):
+        self._check("ba_cuda_attach_device_stream", self.L.ba_cuda_attach_device_stream(self.h, dev, device_ptr, capacity))
+
+    def advance_device_stream(self, dev: int, nbytes: int):
+        self._check("ba_cuda_advance_device_stream", self.L.ba_cuda_advance_device_stream(self.h, dev, nbytes))
+
+    # ---- one pass of the hot path
+    def process(self) -> int:
+        return self._check("ba_cuda_process", self.L.ba_cuda_process(self.h))
+
+    def collect_raw(self, ticket: int, dev: int) -> abi.StepOut:
+        out = abi.StepOut()
+        self._check("ba_cuda_collect", self.L.ba_cuda_collect(self.h, ticket, dev, C.byref(out)))
+        return out
+
+    def collect(self, ticket: int, dev: int) -> StepResult:
+        return StepResult(self.collect_raw(ticket, dev))
+
+    def ticket_ms(self, ticket: int) -> float:
+        ms = C.c_float()
+        self._check("ba_cuda_ticket_ms", self.L.ba_cuda_ticket_ms(self.h, ticket, C.byref(ms)))
+        return ms.value
+
+    def kernel_ms(self, ticket: int):
+        ms = (C.c_float * 2)()
+        self._check("ba_cuda_kernel_ms", self.L.ba_cuda_kernel_ms(self.h, ticket, ms))
+        return ms[0], ms[1]
+
+    def step_bytes(self, ticket: int):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check("ba_cuda_step_bytes", self.L.ba_cuda_step_bytes(self.h, ticket, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        self._check("ba_cuda_launch_count", self.L.ba_cuda_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    # ---- inspection / parity hooks
+    def channel_info(self, dev: int, ch: int) -> abi.ChannelInfo:
+        info = abi.ChannelInfo()
+        self._check("ba_cuda_channel_info", self.L.ba_cuda_channel_info(self.h, dev, ch, C.byref(info)))
+        return info
+
+    def window(self) -> np.ndarray:
+        w = np.empty(self.cfg.fft_size, np.float32)
+        self._check("ba_cuda_window", self.L.ba_cuda_window(self.h, w.ctypes.data_as(C.POINTER(C.c_float)), w.size))
+        return w
+
+    def debug_frames(self, dev: int, iq: np.ndarray, n_frames: int, want_in=True, want_out=True):
+        iq = np.ascontiguousarray(iq)
+        n = self.cfg.fft_size
+        fi = np.empty((n_frames, n, 2), np.float32) if want_in else None
+        fo = np.empty((n_frames, n, 2), np.float32) if want_out else None
+        self._check("ba_cuda_debug_frames", self.L.ba_cuda_debug_frames(
+            self.h, dev, iq.ctypes.data, iq.nbytes, n_frames, None if fi is None else fi.ctypes.data, None if fo is None else fo.ctypes.data))
+        return fi, fo
+
+    def debug_picks(self, dev: int, ch: int, first: int, count: int) -> np.ndarray:
+        out = np.empty((count, 2), np.float32)
+        self._check("ba_cuda_debug_picks", self.L.ba_cuda_debug_picks(self.h, dev, ch, first, count, out.ctypes.data))
+        return out
+
+    def inject_picks(self, dev: int, picks: np.ndarray):
+        """picks: [n_frames][channels][2] float32 (test hook, see ba_cuda_debug_inject_picks)."""
+        picks = np.ascontiguousarray(picks, np.float32)
+        self._check("ba_cuda_debug_inject_picks", self.L.ba_cuda_debug_inject_picks(self.h, dev, picks.ctypes.data, picks.shape[0]))
+
+    # ---- convenience: run a whole in-memory stream through the engine, as a file input would
+    def run_stream(self, streams: List[np.ndarray], chunk_bytes: Optional[int] = None):
+        """Feed streams[dev] (interleaved IQ arrays) in ring-sized chunks and return, per device, a dict with the
+        concatenated waveout [C][n], iq_out, trace and the list of per-batch status rows."""
+        nd = len(self.cfg.devices)
+        views = [np.ascontiguousarray(s).view(np.uint8).reshape(-1) for s in streams]
+        pos = [0] * nd
+        acc = [dict(waveout=[], iq_out=[], trace=[], status=[], frames_done=0) for _ in range(nd)]
+        if chunk_bytes is None:
+            chunk_bytes = 1 << 20
+        while True:
+            fed = False
+            for d in range(nd):
+                if pos[d] < views[d].size:
+                    n = min(chunk_bytes, views[d].size - pos[d])
+                    self.submit(d, views[d][pos[d]:pos[d] + n])
+                    pos[d] += n
+                    fed = True
+            t = self.process()
+            produced = False
+            for d in range(nd):
+                r = self.collect(t, d)
+                acc[d]["frames_done"] = r.frames_done
+                if r.n_batches:
+                    produced = True
+                    acc[d]["waveout"].append(r.waveout)
+                    if r.iq_out is not None:
+                        acc[d]["iq_out"].append(r.iq_out)
+                    if r.trace is not None:
+                        acc[d]["trace"].append(r.trace)
+                    for b in range(r.n_batches):
+                        acc[d]["status"].append([r.status(b, c) for c in range(r.channel_count)])
+            if not fed and not produced:
+                break
+        out = []
+        for d in range(nd):
+            a = acc[d]
+            c = len(self.cfg.devices[d].channels)
+            out.append(dict(
+                waveout=np.concatenate(a["waveout"], axis=1) if a["waveout"] else np.zeros((c, 0), np.float32),
+                iq_out=np.concatenate(a["iq_out"], axis=1) if a["iq_out"] else None,
+                trace=np.concatenate(a["trace"], axis=1) if a["trace"] else None,
+                status=a["status"], frames_done=a["frames_done"]))
+        return out

@@ -106,6 +106,7 @@ typedef struct ba_engine_desc {
     const ba_device_desc* devices;
     int32_t max_batches_per_step; /* capacity: WAVE_BATCH batches per device one ba_cuda_process() may produce; 0 = 8 */
     uint32_t flags;               /* BA_FLAG_* */
+    uint64_t ring_bytes;          /* base size of each pinned input ring before rounding; 0 = MIN_BUF_SIZE 2560000 (boondock_airband.h:64) */
 } ba_engine_desc;
 
 /* Per-channel scalars observers read after every batch
@@ -176,6 +177,11 @@ int ba_cuda_submit(ba_engine* e, int dev, const void* iq, size_t bytes);
  * (the rx thread of an unmodified input driver): publishes `bytes` more bytes at the ring's write index. */
 int ba_cuda_commit(ba_engine* e, int dev, size_t bytes);
 
+/* Zero-copy variant for producers that already hold their samples in (ideally pinned) host memory: the bytes are
+ * copied host->device straight from `iq` during the next ba_cuda_process() calls, without passing through the ring.
+ * The memory must stay valid and unchanged until the ticket that consumed it has been collected. */
+int ba_cuda_submit_external(ba_engine* e, int dev, const void* iq, size_t bytes);
+
 /* Device-resident input (benchmarks, GPUDirect producers): the stream lives in HBM at d_iq;
  * ba_cuda_advance_device_stream() says how many more bytes of it are valid. */
 int ba_cuda_attach_device_stream(ba_engine* e, int dev, const void* d_iq, size_t capacity_bytes);
@@ -193,6 +199,9 @@ int ba_cuda_collect(ba_engine* e, int ticket, int dev, ba_step_out* out);
 /* Device time (ms) between the first and last GPU operation of a finished ticket. */
 int ba_cuda_ticket_ms(ba_engine* e, int ticket, float* ms);
 
+/* Bytes the ticket moved host->device (input samples) and device->host (results). */
+int ba_cuda_step_bytes(ba_engine* e, int ticket, uint64_t* h2d, uint64_t* d2h);
+
 int ba_cuda_channel_info(ba_engine* e, int dev, int channel, ba_channel_info* out);
 /* Window as computed at create time, fft_size floats (src/boondock_airband.cpp:357-373). */
 int ba_cuda_window(ba_engine* e, float* out, size_t count);
@@ -204,6 +213,10 @@ int ba_cuda_debug_frames(ba_engine* e, int dev, const void* iq, size_t bytes, in
 /* Copy out the picked-bin IQ series the last finished ticket consumed for one channel:
  * frames [first, first+count) of the device's stream, as (re,im) pairs. */
 int ba_cuda_debug_picks(ba_engine* e, int dev, int channel, uint64_t first, int count, float* out);
+/* Parity hook: append `n_frames` rows of externally computed picked-bin IQ ([n_frames][channel_count][2] floats) to the
+ * device's pick ring as if the channelizer had produced them; the next ba_cuda_process() demodulates them.  Lets the
+ * tests check the demodulator bit for bit on the oracle's own FFT output.  Not to be mixed with byte input. */
+int ba_cuda_debug_inject_picks(ba_engine* e, int dev, const float* picks, int n_frames);
 /* Kernel launch counters since create (all kernels are this library's own). */
 int ba_cuda_launch_count(ba_engine* e, uint64_t* launches);
 /* Per-kernel accumulated device time of the last finished ticket: ms[0]=channelize (K1), ms[1]=demod (K2). */

@@ -1,0 +1,66 @@
+"""Parity scenarios: small versions of the BASELINE.json workloads plus option coverage the reference has no test for."""
+from __future__ import annotations
+
+import numpy as np
+
+from boondock_airband_b200 import abi, configs, synth
+from boondock_airband_b200.abi import ChannelCfg, DeviceCfg, EngineCfg
+
+
+def cfg1_short(seconds=0.9):
+    cfg = configs.cfg1()
+    cfg.flags = abi.FLAG_TRACE
+    cfg.max_batches_per_step = 3
+    iq = synth.synth(cfg.devices[0], seconds, 0, gate_on=0.25, gate_off=0.1)
+    return cfg, [iq]
+
+
+def cfg2_small(n_channels=8, seconds=1.3):
+    cfg = configs.cfg2(n_channels)
+    cfg.flags = abi.FLAG_TRACE
+    cfg.max_batches_per_step = 2
+    iq = synth.synth(cfg.devices[0], seconds, 0, gate_on=0.8, gate_off=0.15)
+    return cfg, [iq]
+
+
+def mixed_options(seconds=0.8, fmt="s16", fft_size=1024, fm_demod=abi.FM_FAST_ATAN2, afc=True):
+    """One input carrying every per-channel option of parse_channels (config.cpp:312-729)."""
+    fs, cf = 2_400_000, 145_000_000
+    ch = [
+        ChannelCfg(freq=cf - 600_000),                                              # plain AM
+        ChannelCfg(freq=cf - 450_000, bandwidth=8000),                              # AM through the low-pass (needs_raw_iq)
+        ChannelCfg(freq=cf - 300_000, modulation="nfm"),                            # NFM, no filters
+        ChannelCfg(freq=cf - 150_000, modulation="nfm", bandwidth=12_500, tau=0),   # NFM, no de-emphasis
+        ChannelCfg(freq=cf + 150_000, modulation="nfm", bandwidth=12_500, ctcss=100.0, notch=100.0, tau=530),
+        ChannelCfg(freq=cf + 300_000, squelch_threshold=-45, ampfactor=2.5),        # manual squelch level, amplified
+        ChannelCfg(freq=cf + 450_000, squelch_snr_threshold=6.0, has_iq_outputs=True),
+        ChannelCfg(freq=cf + 600_000, modulation="nfm", notch=1000.0, notch_q=5.0, has_iq_outputs=True),
+        ChannelCfg(freq=cf + 750_000, afc=8 if afc else 0),                                       # AFC walk
+        ChannelCfg(freq=cf + 900_000 + 4_000, afc=20 if afc else 0, modulation="nfm", bandwidth=12_500),
+    ]
+    dev = DeviceCfg(sample_rate=fs, centerfreq=cf, sample_format=fmt, channels=ch, tau=300)
+    cfg = EngineCfg(fft_size=fft_size, wave_rate=16000, fm_demod=fm_demod, devices=[dev], flags=abi.FLAG_TRACE, max_batches_per_step=2)
+    iq = synth.synth(dev, seconds, 7, gate_on=0.3, gate_off=0.12)
+    return cfg, [iq]
+
+
+def multi_device(seconds=0.5):
+    """Three inputs of different sample formats and rates behind one engine (device_start..device_end of one demod thread)."""
+    devs = []
+    streams = []
+    specs = (("u8", 2_560_000, 120_000_000), ("s8", 2_048_000, 131_000_000), ("f32", 1_920_000, 460_000_000))
+    for i, (fmt, fs, cf) in enumerate(specs):
+        ch = [ChannelCfg(freq=cf + k * 100_000 + 12_500 * i) for k in (-3, -1, 2)]
+        ch.append(ChannelCfg(freq=cf + 350_000, bandwidth=6000))
+        d = DeviceCfg(sample_rate=fs, centerfreq=cf, sample_format=fmt, channels=ch)
+        devs.append(d)
+        streams.append(synth.synth(d, seconds * (1.0 + 0.3 * i), 20 + i, gate_on=0.2, gate_off=0.07))
+    cfg = EngineCfg(fft_size=512, wave_rate=8000, devices=devs, flags=abi.FLAG_TRACE, max_batches_per_step=2)
+    return cfg, streams
+
+
+def squelch_steps(levels, fft_size=512):
+    """Picked-bin series with constant magnitudes, the stimulus of test_squelch.cpp (0.05 = noise, 0.75 = signal)."""
+    z = np.zeros((len(levels), 1, 2), np.float32)
+    z[:, 0, 0] = levels
+    return z

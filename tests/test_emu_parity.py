@@ -1,0 +1,69 @@
+"""CPU-side checks of the engine's host logic and kernel index arithmetic through the thread-emulated build of the
+product sources (tests/emu).  These do not replace the GPU parity tests (tests/test_gpu_parity.py, -m gpu); they catch
+logic errors before a B200 is involved.  The emulation library is test infrastructure and is never loaded by the package."""
+import numpy as np
+import pytest
+
+from boondock_airband_b200 import abi
+from boondock_airband_b200.abi import ChannelCfg, DeviceCfg, EngineCfg
+
+import parity
+import scenarios
+
+
+@pytest.fixture(scope="module")
+def emu(oracle_built):
+    return parity.lib_for("emu")
+
+
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("fmt", ["u8", "s8", "s16", "f32"])
+def test_emu_frames(emu, n, fmt):
+    rng = np.random.default_rng(n + len(fmt))
+    dev = DeviceCfg(sample_rate=2_400_000, centerfreq=100_000_000, sample_format=fmt,
+                    channels=[ChannelCfg(freq=100_000_000 + 12_500 * k) for k in range(-5, 6)])
+    cfg = EngineCfg(fft_size=n, wave_rate=16000, devices=[dev])
+    nfr = 9
+    iq = parity.random_iq(rng, fmt, 150 * (nfr - 1) + n + 3)
+    parity.check_frames(cfg, iq, nfr, emu)
+
+
+def test_emu_u8_all_codes(emu):
+    """Every u8 code converts to exactly (i - 127.5f) / 127.5f times the window (boondock_airband.cpp:341-343)."""
+    dev = DeviceCfg(sample_rate=2_560_000, centerfreq=120_000_000, channels=[ChannelCfg(freq=120_100_000)])
+    cfg = EngineCfg(fft_size=256, wave_rate=8000, devices=[dev])
+    iq = np.repeat(np.arange(256, dtype=np.uint8), 2)[:512]
+    iq = np.concatenate([iq, iq[::-1]]).astype(np.uint8)
+    iq = np.resize(iq, 2 * (320 * 3 + 256))
+    parity.check_frames(cfg, iq, 4, emu)
+
+
+def test_emu_cfg1(emu):
+    cfg, streams = scenarios.cfg1_short(0.9)
+    o, res, _ = parity.run_both(cfg, streams, emu, chunk_bytes=700_001)
+    parity.compare_streams(cfg, o, res, min_open=1000)
+
+
+def test_emu_cfg2(emu):
+    cfg, streams = scenarios.cfg2_small(6, 1.1)
+    o, res, _ = parity.run_both(cfg, streams, emu, chunk_bytes=1_000_003)
+    parity.compare_streams(cfg, o, res, min_open=1000)
+
+
+@pytest.mark.parametrize("fm_demod", [abi.FM_FAST_ATAN2, abi.FM_QUADRI_DEMOD])
+def test_emu_mixed_options_exact(emu, fm_demod):
+    cfg, streams = scenarios.mixed_options(0.7, fm_demod=fm_demod, afc=False)  # AFC needs K1's spectrum: end-to-end test below
+    parity.check_channel_info(cfg, emu)
+    parity.check_demod_exact(cfg, streams, emu, frames_per_call=1777)
+
+
+def test_emu_mixed_options_end_to_end(emu):
+    cfg, streams = scenarios.mixed_options(0.7)
+    o, res, _ = parity.run_both(cfg, streams, emu, chunk_bytes=555_555)
+    parity.compare_streams(cfg, o, res, min_open=1000)
+
+
+def test_emu_multi_device(emu):
+    cfg, streams = scenarios.multi_device(0.5)
+    o, res, _ = parity.run_both(cfg, streams, emu, chunk_bytes=300_000)
+    parity.compare_streams(cfg, o, res, min_open=500)
