@@ -295,7 +295,7 @@ def main():
             h.copy_(tmpl[i][: step_bytes + lead])
             host.append(h)
         # every input gets its own pinned buffer (no sharing of host pages between inputs)
-        hbuf = [host[i].clone().pin_memory() if i >= TEMPLATES else host[i] for i in range(args.inputs)]
+        hbuf = [host[i % TEMPLATES].clone().pin_memory() if i >= TEMPLATES else host[i] for i in range(args.inputs)]
         torch.cuda.synchronize()
         h2d = d2h = 0
         pend = []

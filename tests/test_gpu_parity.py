@@ -84,7 +84,7 @@ def test_demod_bit_exact(cuda, fm_demod):
 
 def test_demod_bit_exact_cfg2(cuda):
     cfg, streams = scenarios.cfg2_small(16, 1.6)
-    parity.check_demod_exact(cfg, streams, cuda, frames_per_call=5000)
+    parity.check_demod_exact(cfg, streams, cuda, frames_per_call=3000)
 
 
 def test_mixed_options_end_to_end(cuda):
