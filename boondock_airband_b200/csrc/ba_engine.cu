@@ -87,6 +87,7 @@ struct Dev {
     bool injected = false;
     /* picks, bins */
     float2* d_picks = nullptr;
+    float* d_mags = nullptr;
     uint32_t ring_len = 0;
     uint32_t* d_bins = nullptr;
     float2* d_spectrum = nullptr;
@@ -143,7 +144,7 @@ struct ba_engine {
     Slot slot[2];
     int next_ticket = 0;
     uint64_t launches = 0;
-    int tile_frames = 0, raw_bytes = 0, k1_ctas_per_sm = 1;
+    int tile_frames = 0, raw_bytes = 0, k1_ctas_per_sm = 2;
     size_t desc_bytes = 0;
     int max_phases = 1;
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -164,6 +165,7 @@ void free_engine(ba_engine* e) {
         cudaFree(d->d_buf[0]);
         cudaFree(d->d_buf[1]);
         cudaFree(d->d_picks);
+        cudaFree(d->d_mags);
         cudaFree(d->d_bins);
         cudaFree(d->d_spectrum);
         delete d;
@@ -227,6 +229,7 @@ int setup_channel(ba_engine* e, Dev& d, int ci, ba::K2Chan& k, ba::K2State& st, 
         return fail(BA_ERR_BAD_ARG, "channel %d: unknown modulation %d", ci, cd.modulation);
     k.col = (uint32_t)ci;
     k.picks = d.d_picks;
+    k.mags = d.d_mags;
     k.ring_mask = d.ring_len - 1;
     k.c_pad = (uint32_t)d.c_pad;
     k.bin = d.d_bins + ci;
@@ -478,9 +481,11 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
         d->ring_len = pow2_at_least(frames_cap + BA_E);
         if (cudaMalloc((void**)&d->d_buf[0], d->d_cap) != cudaSuccess || cudaMalloc((void**)&d->d_buf[1], d->d_cap) != cudaSuccess ||
             cudaMalloc((void**)&d->d_picks, sizeof(float2) * (size_t)d->ring_len * d->c_pad) != cudaSuccess ||
+            cudaMalloc((void**)&d->d_mags, sizeof(float) * (size_t)d->ring_len * d->c_pad) != cudaSuccess ||
             cudaMalloc((void**)&d->d_bins, sizeof(uint32_t) * d->c_pad) != cudaSuccess)
             return fail(BA_ERR_NOMEM, "device memory for input %d", di);
         CU(cudaMemset(d->d_picks, 0, sizeof(float2) * (size_t)d->ring_len * d->c_pad));
+        CU(cudaMemset(d->d_mags, 0, sizeof(float) * (size_t)d->ring_len * d->c_pad));
         if (d->any_afc) {
             if (cudaMalloc((void**)&d->d_spectrum, sizeof(float2) * N) != cudaSuccess)
                 return fail(BA_ERR_NOMEM, "device memory for input %d", di);
@@ -852,6 +857,7 @@ int ba_cuda_process(ba_engine* e) {
                 k.n_frames = (uint32_t)(f_end - f_begin);
                 k.frame0 = f_begin;
                 k.picks = d.d_picks;
+                k.mags = d.d_mags;
                 k.ring_mask = d.ring_len - 1;
                 k.c_pad = (uint32_t)d.c_pad;
                 k.n_channels = (uint32_t)d.C;
@@ -1106,6 +1112,7 @@ int ba_cuda_debug_frames(ba_engine* e, int dev, const void* iq, size_t bytes, in
         return fail(BA_ERR_BAD_ARG, "%d frames need %zu bytes, %zu given", n_frames, (size_t)(n_frames - 1) * d->hop_bytes + d->frame_bytes, bytes);
     unsigned char* d_iq = nullptr;
     float2 *d_in = nullptr, *d_out = nullptr, *d_picks = nullptr;
+    float* d_mags = nullptr;
     K1Device* d_k = nullptr;
     const uint32_t ring_len = pow2_at_least((uint64_t)n_frames);
     int rc = BA_OK;
@@ -1114,6 +1121,7 @@ int ba_cuda_debug_frames(ba_engine* e, int dev, const void* iq, size_t bytes, in
         cudaFree(d_in);
         cudaFree(d_out);
         cudaFree(d_picks);
+        cudaFree(d_mags);
         cudaFree(d_k);
     };
 #define CUD(call)                                                                                  \
@@ -1129,6 +1137,7 @@ int ba_cuda_debug_frames(ba_engine* e, int dev, const void* iq, size_t bytes, in
     CUD(cudaMalloc((void**)&d_in, sizeof(float2) * N * n_frames));
     CUD(cudaMalloc((void**)&d_out, sizeof(float2) * N * n_frames));
     CUD(cudaMalloc((void**)&d_picks, sizeof(float2) * (size_t)ring_len * d->c_pad));
+    CUD(cudaMalloc((void**)&d_mags, sizeof(float) * (size_t)ring_len * d->c_pad));
     CUD(cudaMalloc((void**)&d_k, sizeof(K1Device)));
     CUD(cudaMemcpy(d_iq, iq, bytes, cudaMemcpyHostToDevice));
     K1Device k;
@@ -1140,6 +1149,7 @@ int ba_cuda_debug_frames(ba_engine* e, int dev, const void* iq, size_t bytes, in
     k.n_frames = (uint32_t)n_frames;
     k.frame0 = 0;
     k.picks = d_picks;
+    k.mags = d_mags;
     k.ring_mask = ring_len - 1;
     k.c_pad = (uint32_t)d->c_pad;
     k.n_channels = (uint32_t)d->C;
@@ -1206,10 +1216,22 @@ int ba_cuda_debug_inject_picks(ba_engine* e, int dev, const float* picks, int n_
     uint64_t f = d->frames_done;
     int left = n_frames;
     const float* src = picks;
+    /* the magnitudes K1 would have written next to the picks; sqrtf and the products are IEEE operations here too
+     * (this file is host code compiled without fast-math; the volatile keeps the compiler from contracting them) */
+    std::vector<float> mag((size_t)n_frames * d->C);
+    for (size_t i = 0; i < mag.size(); i++) {
+        volatile float rr = picks[2 * i] * picks[2 * i];
+        volatile float ii = picks[2 * i + 1] * picks[2 * i + 1];
+        volatile float sum = rr + ii;
+        mag[i] = sqrtf(sum);
+    }
+    const float* msrc = mag.data();
     while (left > 0) {
         const uint32_t pos = (uint32_t)(f & (d->ring_len - 1));
         const int n = (int)std::min<uint64_t>((uint64_t)left, d->ring_len - pos);
         CU(cudaMemcpy2D(d->d_picks + (size_t)pos * d->c_pad, sizeof(float2) * d->c_pad, src, sizeof(float2) * d->C, sizeof(float2) * d->C, (size_t)n, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy2D(d->d_mags + (size_t)pos * d->c_pad, sizeof(float) * d->c_pad, msrc, sizeof(float) * d->C, sizeof(float) * d->C, (size_t)n, cudaMemcpyHostToDevice));
+        msrc += (size_t)n * d->C;
         src += 2 * (size_t)n * d->C;
         f += n;
         left -= n;

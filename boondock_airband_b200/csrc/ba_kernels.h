@@ -30,6 +30,7 @@ struct K1Device {
     uint32_t n_frames;       /* frames in this launch */
     uint64_t frame0;         /* stream index of frame 0 */
     float2* picks;           /* [ring_len][c_pad]: fftout[bins[c]] per frame, ring over frames */
+    float* mags;             /* [ring_len][c_pad]: |fftout[bins[c]]| = wavein[] as the bin pick writes it (.cpp:507-513) */
     uint32_t ring_mask;      /* ring_len - 1 */
     uint32_t c_pad;
     uint32_t n_channels;
@@ -76,6 +77,7 @@ struct K2Chan {
     int32_t dev;          /* input index (K2Dyn) */
     uint32_t col;         /* channel index within its input = column of the pick row */
     const float2* picks;  /* its input's pick ring */
+    const float* mags;    /* magnitudes of the same picks */
     uint32_t ring_mask, c_pad;
     uint32_t* bin;        /* &bins[col] (AFC moves it) */
     uint32_t base_bin;

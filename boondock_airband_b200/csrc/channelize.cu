@@ -291,8 +291,13 @@ __device__ __forceinline__ void run_tile_frames(const ThreadConst<N>& tc, const 
         if (live) {
             const uint64_t fs = d.frame0 + (uint64_t)f;
             float2* row = d.picks + (size_t)(fs & d.ring_mask) * d.c_pad;
-            for (int c = t; c < (int)d.n_channels; c += GE::G)
-                row[c] = work[picktab[c]];
+            float* mrow = d.mags + (size_t)(fs & d.ring_mask) * d.c_pad;
+            for (int c = t; c < (int)d.n_channels; c += GE::G) {
+                const float2 v = work[picktab[c]];
+                row[c] = v;
+                /* wavein[] = sqrtf(re*re + im*im), boondock_airband.cpp:507-513: three separately rounded operations and an IEEE square root */
+                mrow[c] = __fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)));
+            }
             if (d.dbg_out) {
                 float2* o = d.dbg_out + (size_t)f * N;
                 for (int k = t; k < N; k += GE::G)

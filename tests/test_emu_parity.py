@@ -44,6 +44,16 @@ def test_emu_cfg1(emu):
     parity.compare_streams(cfg, o, res, min_open=1000)
 
 
+def test_emu_cfg1_fast_path(emu):
+    """Without the trace flag plain AM channels take the specialised (PLAIN) instantiation of the demodulator."""
+    cfg, streams = scenarios.cfg1_short(0.9)
+    cfg.flags = 0
+    o, res, _ = parity.run_both(cfg, streams, emu, chunk_bytes=700_001)
+    assert res[0]["trace"] is None
+    parity.compare_streams(cfg, o, res)
+    assert float(np.abs(res[0]["waveout"]).max()) > 0.05
+
+
 def test_emu_cfg2(emu):
     cfg, streams = scenarios.cfg2_small(6, 1.1)
     o, res, _ = parity.run_both(cfg, streams, emu, chunk_bytes=1_000_003)

@@ -56,6 +56,38 @@ def test_cfg1(cuda):
     assert launches > 0
 
 
+def test_cfg1_fast_path(cuda):
+    """Without the trace flag plain AM channels take the specialised (PLAIN) instantiation of the demodulator."""
+    cfg, streams = scenarios.cfg1_short(2.1)
+    cfg.flags = 0
+    o, res, _ = parity.run_both(cfg, streams, cuda, chunk_bytes=700_001)
+    assert res[0]["trace"] is None
+    parity.compare_streams(cfg, o, res)
+    assert float(np.abs(res[0]["waveout"]).max()) > 0.05
+
+
+def test_fast_path_bit_exact(cuda):
+    """The PLAIN instantiation fed with the oracle's picks: audio and levels bit-exact (trace is compared through the audio gate)."""
+    cfg, streams = scenarios.cfg1_short(1.2)
+    from oracle.ba_oracle import Oracle
+    o = Oracle(cfg)
+    o.feed(0, streams[0])
+    picks = np.stack([o.picks(0, c) for c in range(8)], axis=1)
+    cfg.flags = 0
+    e = Engine(cfg, cuda)
+    waves = []
+    for lo in range(0, picks.shape[0], 2500):
+        e.inject_picks(0, picks[lo:lo + 2500])
+        t = e.process()
+        r = e.collect(t, 0)
+        if r.n_batches:
+            waves.append(r.waveout)
+    e.close()
+    got = np.concatenate(waves, axis=1)
+    for c in range(8):
+        assert np.array_equal(got[c].view(np.uint32), o.waveout(0, c).view(np.uint32)), c
+
+
 def test_cfg1_picks(cuda):
     cfg, streams = scenarios.cfg1_short(0.4)
     parity.check_picks(cfg, streams[0][:2_000_000], cuda)
