@@ -64,50 +64,57 @@ def dist_env():
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled through NVML every 10 ms while the GPU is under load
+    (the same fields as the nvidia-smi line of B200_PROFILING.md; nvidia-smi -lms is too slow for a sub-second region)."""
 
     def __init__(self, index: int):
         self.index = index
         self.rows = []
-        self.proc = None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception as ex:  # noqa: BLE001
+            self.err = repr(ex)
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 9:
-                continue
+        nv = self.nv
+        while not self.stop_flag.is_set():
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((time.perf_counter(), sm, rs))
+            except Exception as ex:  # noqa: BLE001
+                self.err = repr(ex)
+                return
+            time.sleep(0.01)
+
+    def stop(self, windows=None):
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: %s" % self.err]}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        nv = self.nv
+        names = (("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8)), ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                 ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)), ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+        rows = self.rows
+        if windows:
+            rows = [r for r in rows if any(a <= r[0] <= b for (a, b) in windows)]
+        sm = [r[1] for r in rows]
+        reasons = sorted({n for r in rows for (n, bit) in names if r[2] & bit})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(sm),
+                "window": "timed regions (device-resident + end-to-end), NVML every 10 ms"}
 
 
 def workload_cfg(n_inputs: int, fft_size: int, first_index: int, cuda_device: int):
@@ -260,19 +267,20 @@ def main():
             batches += r.n_batches
         return k1, k2, batches
 
+    sampler = ClockSampler(local)
+    sampler.start()
     run_steps(W, True)
     launches0 = eng.launch_count()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     eng.mark(0)
     t0 = time.perf_counter()
     k1_ms, k2_ms, batches = run_steps(K, False)
     eng.mark(1)
     barrier()
-    wall = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    wall = t1 - t0
     dev_ms = eng.mark_ms(0, 1)
-    clocks = sampler.stop()
+    windows = [(t0, t1)]
     launches = eng.launch_count() - launches0
     assert batches == K * BATCHES_PER_STEP, "device-resident run produced %d batches, expected %d" % (batches, K * BATCHES_PER_STEP)
     elapsed = max(wall, dev_ms / 1e3)
@@ -330,6 +338,7 @@ def main():
         got = e2e_steps(K, False)
         barrier()
         e2e_wall = time.perf_counter() - t0
+        windows.append((t0, t0 + e2e_wall))
         assert got == K * BATCHES_PER_STEP, "end-to-end run produced %d batches, expected %d" % (got, K * BATCHES_PER_STEP)
         if world > 1:
             tt = torch.tensor([e2e_wall], dtype=torch.float64, device=device)
@@ -340,6 +349,7 @@ def main():
                "ms_per_step": 1e3 * e2e_wall / K, "path": "ba_cuda_submit_external (pinned host) -> ba_cuda_process -> ba_cuda_collect"}
         eng2.close()
 
+    clocks = sampler.stop(windows)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

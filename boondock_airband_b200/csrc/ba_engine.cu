@@ -110,8 +110,11 @@ struct Slot {
     ba_channel_status* h_status = nullptr;
     unsigned char* d_desc = nullptr;
     unsigned char* h_desc = nullptr;
-    cudaEvent_t ev_begin = nullptr, ev_done = nullptr;
-    std::vector<cudaEvent_t> ev_k; /* 3 per phase: before K1, between, after K2 */
+    cudaEvent_t ev_begin = nullptr, ev_done = nullptr; /* first operation of the ticket / results are in pinned host memory */
+    cudaEvent_t ev_in = nullptr, ev_kdone = nullptr;    /* inputs and descriptors are in HBM / kernels have finished */
+    cudaEvent_t ev_k1 = nullptr;                        /* the channelizer of the last phase has finished */
+    bool used = false;
+    std::vector<cudaEvent_t> ev_k; /* 4 per phase: before/after K1, before/after K2 */
     int phases = 0;
     int ticket = -1;
     bool busy = false;
@@ -130,7 +133,9 @@ struct ba_engine {
     int total_channels = 0, max_channels = 0;
     int stride = 0; /* max_batches*B + E */
     bool any_iq = false, any_afc = false;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr; /* = s_k: kernels; debug helpers run here */
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_k2 = nullptr, s_out = nullptr; /* host->device, K1, K2, device->host */
+    cudaEvent_t ev_tmp[2] = {nullptr, nullptr};
     float* d_window = nullptr;
     float2* d_twiddle = nullptr;
     float* d_sincos = nullptr;
@@ -155,8 +160,9 @@ namespace {
 void free_engine(ba_engine* e) {
     if (!e)
         return;
-    if (e->stream)
-        cudaStreamSynchronize(e->stream);
+    for (cudaStream_t q : {e->s_in, e->s_k, e->s_k2, e->s_out})
+        if (q)
+            cudaStreamSynchronize(q);
     for (Dev* d : e->dev) {
         if (!d)
             continue;
@@ -190,6 +196,12 @@ void free_engine(ba_engine* e) {
             cudaEventDestroy(s.ev_begin);
         if (s.ev_done)
             cudaEventDestroy(s.ev_done);
+        if (s.ev_in)
+            cudaEventDestroy(s.ev_in);
+        if (s.ev_kdone)
+            cudaEventDestroy(s.ev_kdone);
+        if (s.ev_k1)
+            cudaEventDestroy(s.ev_k1);
         for (cudaEvent_t ev : s.ev_k)
             cudaEventDestroy(ev);
     }
@@ -203,8 +215,12 @@ void free_engine(ba_engine* e) {
     cudaFree(e->d_state);
     cudaFree(e->d_ctcss);
     cudaFree(e->d_order);
-    if (e->stream)
-        cudaStreamDestroy(e->stream);
+    for (cudaStream_t q : {e->s_in, e->s_k, e->s_k2, e->s_out})
+        if (q)
+            cudaStreamDestroy(q);
+    for (cudaEvent_t ev : e->ev_tmp)
+        if (ev)
+            cudaEventDestroy(ev);
     delete e;
 }
 
@@ -417,7 +433,13 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
     e->stride = e->max_batches * e->B + BA_E;
     CU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, desc->cuda_device));
     CU(cudaDeviceGetAttribute(&e->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, desc->cuda_device));
-    CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&e->s_k, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&e->s_k2, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    e->stream = e->s_k;
+    CU(cudaEventCreateWithFlags(&e->ev_tmp[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&e->ev_tmp[1], cudaEventDisableTiming));
 
     /* window, twiddles, sine/cosine table */
     e->window.resize(N);
@@ -478,7 +500,8 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
         memset(d->ring, 0, d->buf_size + d->mirror);
         /* HBM: stream window (two halves), pick ring, bins */
         d->d_cap = (size_t)(frames_cap + 2) * d->hop_bytes + 2 * d->frame_bytes + 64;
-        d->ring_len = pow2_at_least(frames_cap + BA_E);
+        /* two tickets may be in flight on the pick ring: the demodulator of one reads behind the channelizer of the next */
+        d->ring_len = pow2_at_least((uint64_t)(2 * e->max_batches + 1) * e->B + 2 * BA_E);
         if (cudaMalloc((void**)&d->d_buf[0], d->d_cap) != cudaSuccess || cudaMalloc((void**)&d->d_buf[1], d->d_cap) != cudaSuccess ||
             cudaMalloc((void**)&d->d_picks, sizeof(float2) * (size_t)d->ring_len * d->c_pad) != cudaSuccess ||
             cudaMalloc((void**)&d->d_mags, sizeof(float) * (size_t)d->ring_len * d->c_pad) != cudaSuccess ||
@@ -568,7 +591,10 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
             }
             CU(cudaEventCreate(&s.ev_begin));
             CU(cudaEventCreate(&s.ev_done));
-            s.ev_k.resize(3 * (size_t)e->max_phases);
+            CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s.ev_kdone, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s.ev_k1, cudaEventDisableTiming));
+            s.ev_k.resize(4 * (size_t)e->max_phases);
             for (cudaEvent_t& ev : s.ev_k)
                 CU(cudaEventCreate(&ev));
             s.n_batches.assign(nd, 0);
@@ -710,10 +736,16 @@ int ba_cuda_process(ba_engine* e) {
         CU(cudaEventSynchronize(s.ev_done));
         s.busy = false;
     }
+    if (s.used) {
+        /* this slot last served ticket-2: the input half-buffers and descriptors it read are rewritten below (wait for its
+         * kernels), its output arena is rewritten by this ticket's demodulator (wait for its device->host copies) */
+        CU(cudaStreamWaitEvent(e->s_in, s.ev_kdone, 0));
+        CU(cudaStreamWaitEvent(e->any_afc ? e->s_k : e->s_k2, s.ev_done, 0));
+    }
     const size_t nd = e->dev.size();
     const int B = e->B;
     s.h2d_bytes = s.d2h_bytes = 0;
-    CU(cudaEventRecord(s.ev_begin, e->stream));
+    CU(cudaEventRecord(s.ev_begin, e->s_in));
 
     /* 1. move new bytes to HBM and decide how many frames and batches every input runs */
     std::vector<size_t> ring_taken(nd, 0);
@@ -757,20 +789,20 @@ int ba_cuda_process(ba_engine* e) {
             if (take_ring || !take_ext.empty()) {
                 const int nxt = d.cur ^ 1;
                 if (carry)
-                    CU(cudaMemcpyAsync(d.d_buf[nxt], d.d_buf[d.cur] + lo, carry, cudaMemcpyDeviceToDevice, e->stream));
+                    CU(cudaMemcpyAsync(d.d_buf[nxt], d.d_buf[d.cur] + lo, carry, cudaMemcpyDeviceToDevice, e->s_in));
                 size_t at = carry;
                 if (take_ring) {
                     const size_t first = std::min(take_ring, d.buf_size - d.bufs);
-                    CU(cudaMemcpyAsync(d.d_buf[nxt] + at, d.ring + d.bufs, first, cudaMemcpyHostToDevice, e->stream));
+                    CU(cudaMemcpyAsync(d.d_buf[nxt] + at, d.ring + d.bufs, first, cudaMemcpyHostToDevice, e->s_in));
                     if (take_ring > first)
-                        CU(cudaMemcpyAsync(d.d_buf[nxt] + at + first, d.ring, take_ring - first, cudaMemcpyHostToDevice, e->stream));
+                        CU(cudaMemcpyAsync(d.d_buf[nxt] + at + first, d.ring, take_ring - first, cudaMemcpyHostToDevice, e->s_in));
                     at += take_ring;
                     s.h2d_bytes += take_ring;
                     ring_taken[di] = take_ring;
                     any_ring = true;
                 }
                 for (const ExtChunk& c : take_ext) {
-                    CU(cudaMemcpyAsync(d.d_buf[nxt] + at, c.p, c.n, cudaMemcpyHostToDevice, e->stream));
+                    CU(cudaMemcpyAsync(d.d_buf[nxt] + at, c.p, c.n, cudaMemcpyHostToDevice, e->s_in));
                     at += c.n;
                     s.h2d_bytes += c.n;
                 }
@@ -796,7 +828,7 @@ int ba_cuda_process(ba_engine* e) {
     }
     if (any_ring) {
         /* the pinned rings are read by the copy engine: give the bytes back to the producers (bufs, .cpp:735) only once the copies are done */
-        CU(cudaStreamSynchronize(e->stream));
+        CU(cudaStreamSynchronize(e->s_in));
         for (size_t di = 0; di < nd; di++)
             if (ring_taken[di]) {
                 Dev& d = *e->dev[di];
@@ -886,11 +918,17 @@ int ba_cuda_process(ba_engine* e) {
             }
         }
     }
-    CU(cudaMemcpyAsync(s.d_desc, s.h_desc, e->desc_bytes, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(s.d_desc, s.h_desc, e->desc_bytes, cudaMemcpyHostToDevice, e->s_in));
 
-    /* 3. launches */
+    CU(cudaEventRecord(s.ev_in, e->s_in));
+    CU(cudaStreamWaitEvent(e->s_k, s.ev_in, 0));
+
+    /* 3. launches.  The channelizer (FP32/shared-memory bound, fills the SMs) and the demodulator (a latency-bound serial
+     * recurrence, one or two warps per SM) run on two streams: the demodulator of ticket t overlaps the channelizer of
+     * ticket t+1, which writes a disjoint stretch of the pick ring.  With AFC the bins feed back, so one stream is used. */
+    cudaStream_t k2s = e->any_afc ? e->s_k : e->s_k2;
     for (int ph = 0; ph < phases; ph++) {
-        CU(cudaEventRecord(s.ev_k[3 * ph + 0], e->stream));
+        CU(cudaEventRecord(s.ev_k[4 * ph + 0], e->s_k));
         if (k1_count[ph]) {
             K1Params p;
             p.dev = d_k1 + (size_t)ph * nd;
@@ -902,12 +940,17 @@ int ba_cuda_process(ba_engine* e) {
             p.raw_bytes = e->raw_bytes;
             p.max_channels = e->max_channels;
             const int ctas = std::min(p.n_tiles, e->sm_count * e->k1_ctas_per_sm);
-            int rc = k1_launch(e->fft_size, p, ctas, e->stream);
+            int rc = k1_launch(e->fft_size, p, ctas, e->s_k);
             if (rc != 0)
                 return fail(BA_ERR_CUDA, "channelize launch: %s", cudaGetErrorString((cudaError_t)rc));
             e->launches++;
         }
-        CU(cudaEventRecord(s.ev_k[3 * ph + 1], e->stream));
+        CU(cudaEventRecord(s.ev_k[4 * ph + 1], e->s_k));
+        if (k2s != e->s_k) {
+            CU(cudaEventRecord(s.ev_k1, e->s_k));
+            CU(cudaStreamWaitEvent(k2s, s.ev_k1, 0));
+        }
+        CU(cudaEventRecord(s.ev_k[4 * ph + 2], k2s));
         if (k2_any[ph]) {
             K2Params p;
             p.chan = e->d_chan;
@@ -917,14 +960,17 @@ int ba_cuda_process(ba_engine* e) {
             p.n_channels = e->total_channels;
             p.wave_batch = B;
             p.sincos = e->d_sincos;
-            int rc = k2_launch(p, e->stream);
+            int rc = k2_launch(p, k2s);
             if (rc != 0)
                 return fail(BA_ERR_CUDA, "demod launch: %s", cudaGetErrorString((cudaError_t)rc));
             e->launches++;
         }
-        CU(cudaEventRecord(s.ev_k[3 * ph + 2], e->stream));
+        CU(cudaEventRecord(s.ev_k[4 * ph + 3], k2s));
     }
     s.phases = phases;
+
+    CU(cudaEventRecord(s.ev_kdone, k2s));
+    CU(cudaStreamWaitEvent(e->s_out, s.ev_kdone, 0));
 
     /* 4. results to pinned host memory */
     {
@@ -935,10 +981,10 @@ int ba_cuda_process(ba_engine* e) {
         auto copy_rows = [&](size_t off, size_t rows, int nb) -> int {
             const size_t width = (size_t)nb * B;
             CU(cudaMemcpy2DAsync(s.h_wave + off, sizeof(float) * e->stride, s.d_wave + off, sizeof(float) * e->stride, sizeof(float) * width, rows, cudaMemcpyDeviceToHost,
-                                 e->stream));
+                                 e->s_out));
             s.d2h_bytes += sizeof(float) * width * rows;
             if (s.d_trace) {
-                CU(cudaMemcpy2DAsync(s.h_trace + off, e->stride, s.d_trace + off, e->stride, width, rows, cudaMemcpyDeviceToHost, e->stream));
+                CU(cudaMemcpy2DAsync(s.h_trace + off, e->stride, s.d_trace + off, e->stride, width, rows, cudaMemcpyDeviceToHost, e->s_out));
                 s.d2h_bytes += width * rows;
             }
             return BA_OK;
@@ -963,7 +1009,7 @@ int ba_cuda_process(ba_engine* e) {
             if (s.d_iq && d->any_iq) {
                 const size_t width = (size_t)d->step_batches * B;
                 CU(cudaMemcpy2DAsync(s.h_iq + d->iq_off, sizeof(float2) * e->stride, s.d_iq + d->iq_off, sizeof(float2) * e->stride, sizeof(float2) * width, (size_t)d->C,
-                                     cudaMemcpyDeviceToHost, e->stream));
+                                     cudaMemcpyDeviceToHost, e->s_out));
                 s.d2h_bytes += sizeof(float2) * width * d->C;
             }
         }
@@ -974,11 +1020,11 @@ int ba_cuda_process(ba_engine* e) {
             size_t total_status = 0;
             for (Dev* d : e->dev)
                 total_status += (size_t)d->C * e->max_batches;
-            CU(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(ba_channel_status) * total_status, cudaMemcpyDeviceToHost, e->stream));
+            CU(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(ba_channel_status) * total_status, cudaMemcpyDeviceToHost, e->s_out));
             s.d2h_bytes += sizeof(ba_channel_status) * total_status;
         }
     }
-    CU(cudaEventRecord(s.ev_done, e->stream));
+    CU(cudaEventRecord(s.ev_done, e->s_out));
 
     for (size_t di = 0; di < nd; di++) {
         Dev& d = *e->dev[di];
@@ -989,6 +1035,7 @@ int ba_cuda_process(ba_engine* e) {
     }
     s.ticket = ticket;
     s.busy = true;
+    s.used = true;
     e->next_ticket++;
     return ticket;
 }
@@ -1043,8 +1090,8 @@ int ba_cuda_kernel_ms(ba_engine* e, int ticket, float ms[2]) {
     ms[0] = ms[1] = 0.0f;
     for (int ph = 0; ph < s->phases; ph++) {
         float a = 0, b = 0;
-        CU(cudaEventElapsedTime(&a, s->ev_k[3 * ph + 0], s->ev_k[3 * ph + 1]));
-        CU(cudaEventElapsedTime(&b, s->ev_k[3 * ph + 1], s->ev_k[3 * ph + 2]));
+        CU(cudaEventElapsedTime(&a, s->ev_k[4 * ph + 0], s->ev_k[4 * ph + 1]));
+        CU(cudaEventElapsedTime(&b, s->ev_k[4 * ph + 2], s->ev_k[4 * ph + 3]));
         ms[0] += a;
         ms[1] += b;
     }
@@ -1067,7 +1114,11 @@ int ba_cuda_mark(ba_engine* e, int which) {
         return fail(BA_ERR_BAD_ARG, "bad mark %d", which);
     if (!e->marks[which])
         CU(cudaEventCreate(&e->marks[which]));
-    CU(cudaEventRecord(e->marks[which], e->stream));
+    for (cudaStream_t q : {e->s_in, e->s_k, e->s_k2}) {
+        CU(cudaEventRecord(e->ev_tmp[0], q));
+        CU(cudaStreamWaitEvent(e->s_out, e->ev_tmp[0], 0));
+    }
+    CU(cudaEventRecord(e->marks[which], e->s_out));
     return BA_OK;
 }
 
@@ -1132,7 +1183,8 @@ int ba_cuda_debug_frames(ba_engine* e, int dev, const void* iq, size_t bytes, in
             return fail(BA_ERR_CUDA, "%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
         }                                                                                          \
     } while (0)
-    CUD(cudaStreamSynchronize(e->stream));
+    for (cudaStream_t q : {e->s_in, e->s_k, e->s_k2, e->s_out})
+        CUD(cudaStreamSynchronize(q));
     CUD(cudaMalloc((void**)&d_iq, bytes + 1));
     CUD(cudaMalloc((void**)&d_in, sizeof(float2) * N * n_frames));
     CUD(cudaMalloc((void**)&d_out, sizeof(float2) * N * n_frames));
@@ -1192,7 +1244,8 @@ int ba_cuda_debug_picks(ba_engine* e, int dev, int channel, uint64_t first, int 
     if (first + (uint64_t)count > d->frames_done || d->frames_done - first > d->ring_len)
         return fail(BA_ERR_BAD_ARG, "frames [%llu, +%d) are not in the pick ring (frames done %llu, ring %u)", (unsigned long long)first, count,
                     (unsigned long long)d->frames_done, d->ring_len);
-    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(e->s_k));
+    CU(cudaStreamSynchronize(e->s_k2));
     uint64_t f = first;
     int left = count;
     while (left > 0) {
@@ -1212,7 +1265,8 @@ int ba_cuda_debug_inject_picks(ba_engine* e, int dev, const float* picks, int n_
         return fail(BA_ERR_BAD_ARG, "bad argument");
     if ((uint64_t)n_frames > frame_room(e, *d))
         return fail(BA_ERR_OVERRUN, "input %d: room for %llu more frames before the next ba_cuda_process()", dev, (unsigned long long)frame_room(e, *d));
-    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(e->s_k));
+    CU(cudaStreamSynchronize(e->s_k2));
     uint64_t f = d->frames_done;
     int left = n_frames;
     const float* src = picks;
