@@ -67,7 +67,7 @@ struct Dev {
     int C = 0, c_pad = 0;
     size_t sample_bytes = 0; /* one complex sample */
     size_t hop_bytes = 0, frame_bytes = 0;
-    bool any_afc = false, any_iq = false;
+    bool any_afc = false, any_iq = false, any_raw = false;
     int first_chan = 0;
     /* host ring = input_t.buffer */
     std::mutex lock;
@@ -144,6 +144,8 @@ struct ba_engine {
     ba::K2State* d_state = nullptr;
     ba::K2Ctcss* d_ctcss = nullptr;
     int32_t* d_order = nullptr;
+    uint32_t* d_tile_counter = nullptr;
+    int n_plain = 0; /* slots [0, n_plain) of the launch order are plain AM channels */
     std::vector<ba::K2Chan> h_chan;
     std::vector<ba_channel_info> info;
     Slot slot[2];
@@ -215,6 +217,7 @@ void free_engine(ba_engine* e) {
     cudaFree(e->d_state);
     cudaFree(e->d_ctcss);
     cudaFree(e->d_order);
+    cudaFree(e->d_tile_counter);
     for (cudaStream_t q : {e->s_in, e->s_k, e->s_k2, e->s_out})
         if (q)
             cudaStreamDestroy(q);
@@ -244,10 +247,9 @@ int setup_channel(ba_engine* e, Dev& d, int ci, ba::K2Chan& k, ba::K2State& st, 
     if (cd.modulation != BA_MOD_AM && cd.modulation != BA_MOD_NFM)
         return fail(BA_ERR_BAD_ARG, "channel %d: unknown modulation %d", ci, cd.modulation);
     k.col = (uint32_t)ci;
-    k.picks = d.d_picks;
-    k.mags = d.d_mags;
+    k.picks = d.d_picks ? d.d_picks + (size_t)ci * d.ring_len : nullptr;
+    k.mags = d.d_mags + (size_t)ci * d.ring_len;
     k.ring_mask = d.ring_len - 1;
-    k.c_pad = (uint32_t)d.c_pad;
     k.bin = d.d_bins + ci;
     k.fft_size = N;
     k.modulation = cd.modulation;
@@ -349,21 +351,18 @@ int choose_tiles(ba_engine* e) {
     }
     const int groups = ba::k1_groups(N);
     const int fixed = ba::k1_smem_bytes(N, 0, e->max_channels);
-    /* budget: half an SM's shared memory at most so that two CTAs can be resident when registers allow */
-    const int budget = std::min(e->smem_optin, 100 * 1024);
+    /* budget: under half an SM's shared memory so that two CTAs are resident (registers allow it) with room left for the
+     * demodulator's warps; the byte span of a tile is double-buffered */
+    const int budget = std::min(e->smem_optin, 96 * 1024);
+    auto raw_of = [&](int tf) { return (((size_t)(tf - 1) * max_hop + max_frame + 32) + 15) & ~(size_t)15; };
     int tf = 4 * groups;
-    for (;;) {
-        const size_t raw = (size_t)(tf - 1) * max_hop + max_frame + 32;
-        if ((size_t)fixed + raw <= (size_t)budget || tf <= groups)
-            break;
+    while (tf > groups && (size_t)fixed + 2 * raw_of(tf) > (size_t)budget)
         tf -= groups;
-    }
-    if (tf < 1)
-        tf = 1;
-    size_t raw = (size_t)(tf - 1) * max_hop + max_frame + 32;
-    raw = (raw + 15) & ~(size_t)15;
-    if ((size_t)fixed + raw > (size_t)e->smem_optin)
-        return fail(BA_ERR_NOMEM, "K1 needs %zu bytes of shared memory per CTA, the device offers %d", (size_t)fixed + raw, e->smem_optin);
+    while (tf > 1 && (size_t)fixed + 2 * raw_of(tf) > (size_t)e->smem_optin)
+        tf--;
+    const size_t raw = raw_of(tf);
+    if ((size_t)fixed + 2 * raw > (size_t)e->smem_optin)
+        return fail(BA_ERR_NOMEM, "K1 needs %zu bytes of shared memory per CTA, the device offers %d", (size_t)fixed + 2 * raw, e->smem_optin);
     e->tile_frames = tf;
     e->raw_bytes = (int)raw;
     return BA_OK;
@@ -399,8 +398,8 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
     const int N = desc->fft_size;
     if (N < 256 || N > 8192 || (N & (N - 1)))
         return fail(BA_ERR_BAD_SIZE, "fft_size %d is not a power of two in 256..8192", N);
-    if (desc->wave_rate <= 0 || desc->wave_rate % 8)
-        return fail(BA_ERR_BAD_ARG, "wave_rate %d", desc->wave_rate);
+    if (desc->wave_rate <= 0 || desc->wave_rate % 32) /* WAVE_BATCH = wave_rate / 8 samples move in quads */
+        return fail(BA_ERR_BAD_ARG, "wave_rate %d is not a positive multiple of 32", desc->wave_rate);
     if (desc->device_count <= 0 || !desc->devices)
         return fail(BA_ERR_BAD_ARG, "no devices");
     int visible = 0;
@@ -487,6 +486,8 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
                 d->any_afc = true;
             if (c.has_iq_outputs)
                 d->any_iq = true;
+            if (c.modulation == BA_MOD_NFM || c.bandwidth > 0 || c.has_iq_outputs) /* needs_raw_iq, config.cpp:162,596,674-680 */
+                d->any_raw = true;
             if (c.ctcss > 0)
                 n_ctcss++;
         }
@@ -502,13 +503,16 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
         d->d_cap = (size_t)(frames_cap + 2) * d->hop_bytes + 2 * d->frame_bytes + 64;
         /* two tickets may be in flight on the pick ring: the demodulator of one reads behind the channelizer of the next */
         d->ring_len = pow2_at_least((uint64_t)(2 * e->max_batches + 1) * e->B + 2 * BA_E);
+        /* picked-bin IQ is kept only where a demodulator reads it (or a test asked for it); magnitudes always */
+        const bool keep_picks = d->any_raw || (e->flags & BA_FLAG_KEEP_PICKS);
         if (cudaMalloc((void**)&d->d_buf[0], d->d_cap) != cudaSuccess || cudaMalloc((void**)&d->d_buf[1], d->d_cap) != cudaSuccess ||
-            cudaMalloc((void**)&d->d_picks, sizeof(float2) * (size_t)d->ring_len * d->c_pad) != cudaSuccess ||
-            cudaMalloc((void**)&d->d_mags, sizeof(float) * (size_t)d->ring_len * d->c_pad) != cudaSuccess ||
+            (keep_picks && cudaMalloc((void**)&d->d_picks, sizeof(float2) * (size_t)d->ring_len * d->C) != cudaSuccess) ||
+            cudaMalloc((void**)&d->d_mags, sizeof(float) * (size_t)d->ring_len * d->C) != cudaSuccess ||
             cudaMalloc((void**)&d->d_bins, sizeof(uint32_t) * d->c_pad) != cudaSuccess)
             return fail(BA_ERR_NOMEM, "device memory for input %d", di);
-        CU(cudaMemset(d->d_picks, 0, sizeof(float2) * (size_t)d->ring_len * d->c_pad));
-        CU(cudaMemset(d->d_mags, 0, sizeof(float) * (size_t)d->ring_len * d->c_pad));
+        if (d->d_picks)
+            CU(cudaMemset(d->d_picks, 0, sizeof(float2) * (size_t)d->ring_len * d->C));
+        CU(cudaMemset(d->d_mags, 0, sizeof(float) * (size_t)d->ring_len * d->C));
         if (d->any_afc) {
             if (cudaMalloc((void**)&d->d_spectrum, sizeof(float2) * N) != cudaSuccess)
                 return fail(BA_ERR_NOMEM, "device memory for input %d", di);
@@ -529,6 +533,7 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
     CU(cudaMalloc((void**)&e->d_state, sizeof(K2State) * TC));
     CU(cudaMalloc((void**)&e->d_ctcss, sizeof(K2Ctcss) * std::max(1, n_ctcss)));
     CU(cudaMalloc((void**)&e->d_order, sizeof(int32_t) * TC));
+    CU(cudaMalloc((void**)&e->d_tile_counter, sizeof(uint32_t)));
     int used_ctcss = 0;
     for (size_t di = 0; di < e->dev.size(); di++) {
         Dev& d = *e->dev[di];
@@ -543,16 +548,24 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
         std::copy(d.base_bins.begin(), d.base_bins.end(), bins.begin());
         CU(cudaMemcpy(d.d_bins, bins.data(), sizeof(uint32_t) * d.c_pad, cudaMemcpyHostToDevice));
     }
-    /* launch order: group channels of one kind together (plain AM, filtered/NFM, CTCSS) so that the lanes of a warp run the same code */
+    /* launch order: group channels of one kind together (plain AM, other AM, filtered/NFM, CTCSS) so that the lanes of a warp
+     * run the same code; plain AM channels come first and go to their own kernel */
     {
         std::vector<int32_t> order(TC);
         for (int i = 0; i < TC; i++)
             order[i] = i;
+        auto plain = [&](int i) {
+            const K2Chan& k = e->h_chan[i];
+            return k.modulation == BA_MOD_AM && !k.needs_raw_iq && !k.notch_on && !k.ctcss && !k.has_iq_outputs && !k.afc && !(e->flags & BA_FLAG_TRACE);
+        };
         auto kind = [&](int i) {
             const K2Chan& k = e->h_chan[i];
-            return (k.ctcss ? 4 : 0) + (k.modulation == BA_MOD_NFM ? 2 : 0) + (k.needs_raw_iq ? 1 : 0);
+            return (plain(i) ? 0 : 1) + (k.ctcss ? 8 : 0) + (k.modulation == BA_MOD_NFM ? 4 : 0) + (k.needs_raw_iq ? 2 : 0);
         };
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return kind(a) < kind(b); });
+        e->n_plain = 0;
+        for (int i = 0; i < TC; i++)
+            e->n_plain += plain(i) ? 1 : 0;
         CU(cudaMemcpy(e->d_order, order.data(), sizeof(int32_t) * TC, cudaMemcpyHostToDevice));
     }
     CU(cudaMemcpy(e->d_chan, e->h_chan.data(), sizeof(K2Chan) * TC, cudaMemcpyHostToDevice));
@@ -699,6 +712,8 @@ int ba_cuda_attach_device_stream(ba_engine* e, int dev, const void* d_iq, size_t
     Dev* d = get_dev(e, dev);
     if (!d || !d_iq)
         return fail(BA_ERR_BAD_ARG, "bad argument");
+    if (reinterpret_cast<uintptr_t>(d_iq) & 15)
+        return fail(BA_ERR_BAD_ARG, "input %d: a device-resident stream must start on a 16-byte boundary", dev);
     if (d->frames_done || d->have)
         return fail(BA_ERR_STATE, "input %d already consumed data", dev);
     d->attached = (const unsigned char*)d_iq;
@@ -876,22 +891,13 @@ int ba_cuda_process(ba_engine* e) {
                 K1Device& k = h_k1[(size_t)ph * nd + k1_count[ph]];
                 memset(&k, 0, sizeof(k));
                 const uint64_t off = f_begin * d.hop_bytes;
-                if (d.attached) {
-                    k.iq = d.attached + off;
-                    k.lo = d.attached;
-                    k.hi = d.attached + d.attached_valid;
-                } else {
-                    k.iq = d.d_buf[d.cur] + (size_t)(off - d.base_off);
-                    k.lo = d.d_buf[d.cur];
-                    k.hi = d.d_buf[d.cur] + d.have;
-                }
+                k.iq = d.attached ? d.attached + off : d.d_buf[d.cur] + (size_t)(off - d.base_off);
                 k.hop_bytes = (uint32_t)d.hop_bytes;
                 k.n_frames = (uint32_t)(f_end - f_begin);
                 k.frame0 = f_begin;
                 k.picks = d.d_picks;
                 k.mags = d.d_mags;
                 k.ring_mask = d.ring_len - 1;
-                k.c_pad = (uint32_t)d.c_pad;
                 k.n_channels = (uint32_t)d.C;
                 k.tile0 = (uint32_t)k1_tiles[ph];
                 k.bins = d.d_bins;
@@ -939,8 +945,10 @@ int ba_cuda_process(ba_engine* e) {
             p.twiddle = e->d_twiddle;
             p.raw_bytes = e->raw_bytes;
             p.max_channels = e->max_channels;
+            p.tile_counter = e->d_tile_counter;
             const int ctas = std::min(p.n_tiles, e->sm_count * e->k1_ctas_per_sm);
-            int rc = k1_launch(e->fft_size, p, ctas, e->s_k);
+            CU(cudaMemsetAsync(e->d_tile_counter, 0, sizeof(uint32_t), e->s_k));
+            int rc = k1_launch(e->fft_size, p, ctas, e->any_afc, e->s_k);
             if (rc != 0)
                 return fail(BA_ERR_CUDA, "channelize launch: %s", cudaGetErrorString((cudaError_t)rc));
             e->launches++;
@@ -960,10 +968,10 @@ int ba_cuda_process(ba_engine* e) {
             p.n_channels = e->total_channels;
             p.wave_batch = B;
             p.sincos = e->d_sincos;
-            int rc = k2_launch(p, k2s);
+            int rc = k2_launch(p, e->n_plain, k2s);
             if (rc != 0)
                 return fail(BA_ERR_CUDA, "demod launch: %s", cudaGetErrorString((cudaError_t)rc));
-            e->launches++;
+            e->launches += (e->n_plain > 0 ? 1 : 0) + (e->total_channels > e->n_plain ? 1 : 0);
         }
         CU(cudaEventRecord(s.ev_k[4 * ph + 3], k2s));
     }
@@ -1185,25 +1193,22 @@ int ba_cuda_debug_frames(ba_engine* e, int dev, const void* iq, size_t bytes, in
     } while (0)
     for (cudaStream_t q : {e->s_in, e->s_k, e->s_k2, e->s_out})
         CUD(cudaStreamSynchronize(q));
-    CUD(cudaMalloc((void**)&d_iq, bytes + 1));
+    CUD(cudaMalloc((void**)&d_iq, bytes + 16));
     CUD(cudaMalloc((void**)&d_in, sizeof(float2) * N * n_frames));
     CUD(cudaMalloc((void**)&d_out, sizeof(float2) * N * n_frames));
-    CUD(cudaMalloc((void**)&d_picks, sizeof(float2) * (size_t)ring_len * d->c_pad));
-    CUD(cudaMalloc((void**)&d_mags, sizeof(float) * (size_t)ring_len * d->c_pad));
+    CUD(cudaMalloc((void**)&d_picks, sizeof(float2) * (size_t)ring_len * d->C));
+    CUD(cudaMalloc((void**)&d_mags, sizeof(float) * (size_t)ring_len * d->C));
     CUD(cudaMalloc((void**)&d_k, sizeof(K1Device)));
     CUD(cudaMemcpy(d_iq, iq, bytes, cudaMemcpyHostToDevice));
     K1Device k;
     memset(&k, 0, sizeof(k));
     k.iq = d_iq;
-    k.lo = d_iq;
-    k.hi = d_iq + bytes;
     k.hop_bytes = (uint32_t)d->hop_bytes;
     k.n_frames = (uint32_t)n_frames;
     k.frame0 = 0;
     k.picks = d_picks;
     k.mags = d_mags;
     k.ring_mask = ring_len - 1;
-    k.c_pad = (uint32_t)d->c_pad;
     k.n_channels = (uint32_t)d->C;
     k.tile0 = 0;
     k.bins = d->d_bins;
@@ -1221,7 +1226,9 @@ int ba_cuda_debug_frames(ba_engine* e, int dev, const void* iq, size_t bytes, in
     p.twiddle = e->d_twiddle;
     p.raw_bytes = e->raw_bytes;
     p.max_channels = e->max_channels;
-    rc = k1_launch(e->fft_size, p, std::min(p.n_tiles, e->sm_count), e->stream);
+    p.tile_counter = e->d_tile_counter;
+    CUD(cudaMemsetAsync(e->d_tile_counter, 0, sizeof(uint32_t), e->stream));
+    rc = k1_launch(e->fft_size, p, std::min(p.n_tiles, e->sm_count), true, e->stream);
     if (rc != 0) {
         cleanup();
         return fail(BA_ERR_CUDA, "channelize launch: %s", cudaGetErrorString((cudaError_t)rc));
@@ -1241,18 +1248,20 @@ int ba_cuda_debug_picks(ba_engine* e, int dev, int channel, uint64_t first, int 
     Dev* d = get_dev(e, dev);
     if (!d || !out || channel < 0 || channel >= d->C || count < 0)
         return fail(BA_ERR_BAD_ARG, "bad argument");
+    if (!d->d_picks)
+        return fail(BA_ERR_STATE, "input %d keeps no picked-bin IQ (create the engine with BA_FLAG_KEEP_PICKS)", dev);
     if (first + (uint64_t)count > d->frames_done || d->frames_done - first > d->ring_len)
         return fail(BA_ERR_BAD_ARG, "frames [%llu, +%d) are not in the pick ring (frames done %llu, ring %u)", (unsigned long long)first, count,
                     (unsigned long long)d->frames_done, d->ring_len);
     CU(cudaStreamSynchronize(e->s_k));
     CU(cudaStreamSynchronize(e->s_k2));
+    const float2* row = d->d_picks + (size_t)channel * d->ring_len;
     uint64_t f = first;
     int left = count;
     while (left > 0) {
         const uint32_t pos = (uint32_t)(f & (d->ring_len - 1));
         const int n = (int)std::min<uint64_t>((uint64_t)left, d->ring_len - pos);
-        CU(cudaMemcpy2D(out + 2 * (f - first), sizeof(float2), d->d_picks + (size_t)pos * d->c_pad + channel, sizeof(float2) * d->c_pad, sizeof(float2), (size_t)n,
-                        cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(out + 2 * (f - first), row + pos, sizeof(float2) * (size_t)n, cudaMemcpyDeviceToHost));
         f += n;
         left -= n;
     }
@@ -1267,30 +1276,36 @@ int ba_cuda_debug_inject_picks(ba_engine* e, int dev, const float* picks, int n_
         return fail(BA_ERR_OVERRUN, "input %d: room for %llu more frames before the next ba_cuda_process()", dev, (unsigned long long)frame_room(e, *d));
     CU(cudaStreamSynchronize(e->s_k));
     CU(cudaStreamSynchronize(e->s_k2));
-    uint64_t f = d->frames_done;
-    int left = n_frames;
-    const float* src = picks;
-    /* the magnitudes K1 would have written next to the picks; sqrtf and the products are IEEE operations here too
-     * (this file is host code compiled without fast-math; the volatile keeps the compiler from contracting them) */
-    std::vector<float> mag((size_t)n_frames * d->C);
-    for (size_t i = 0; i < mag.size(); i++) {
-        volatile float rr = picks[2 * i] * picks[2 * i];
-        volatile float ii = picks[2 * i + 1] * picks[2 * i + 1];
-        volatile float sum = rr + ii;
-        mag[i] = sqrtf(sum);
+    /* [frame][channel] from the caller -> the device's [channel][frame ring]; the magnitudes K1 would have written next to the
+     * picks are computed here: sqrtf and the products are IEEE operations in this host code too (no fast-math; the volatile
+     * keeps the compiler from contracting them) */
+    const size_t C = (size_t)d->C;
+    std::vector<float2> row((size_t)n_frames);
+    std::vector<float> mrow((size_t)n_frames);
+    for (size_t c = 0; c < C; c++) {
+        for (size_t f = 0; f < (size_t)n_frames; f++) {
+            const float re = picks[2 * (f * C + c)], im = picks[2 * (f * C + c) + 1];
+            volatile float rr = re * re;
+            volatile float ii = im * im;
+            volatile float sum = rr + ii;
+            row[f] = make_float2(re, im);
+            mrow[f] = sqrtf(sum);
+        }
+        uint64_t f = d->frames_done;
+        size_t at = 0;
+        int left = n_frames;
+        while (left > 0) {
+            const uint32_t pos = (uint32_t)(f & (d->ring_len - 1));
+            const int n = (int)std::min<uint64_t>((uint64_t)left, d->ring_len - pos);
+            if (d->d_picks)
+                CU(cudaMemcpy(d->d_picks + c * d->ring_len + pos, row.data() + at, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(d->d_mags + c * d->ring_len + pos, mrow.data() + at, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice));
+            f += n;
+            at += (size_t)n;
+            left -= n;
+        }
     }
-    const float* msrc = mag.data();
-    while (left > 0) {
-        const uint32_t pos = (uint32_t)(f & (d->ring_len - 1));
-        const int n = (int)std::min<uint64_t>((uint64_t)left, d->ring_len - pos);
-        CU(cudaMemcpy2D(d->d_picks + (size_t)pos * d->c_pad, sizeof(float2) * d->c_pad, src, sizeof(float2) * d->C, sizeof(float2) * d->C, (size_t)n, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy2D(d->d_mags + (size_t)pos * d->c_pad, sizeof(float) * d->c_pad, msrc, sizeof(float) * d->C, sizeof(float) * d->C, (size_t)n, cudaMemcpyHostToDevice));
-        msrc += (size_t)n * d->C;
-        src += 2 * (size_t)n * d->C;
-        f += n;
-        left -= n;
-    }
-    d->frames_done = f;
+    d->frames_done += (uint64_t)n_frames;
     d->injected = true;
     return BA_OK;
 }

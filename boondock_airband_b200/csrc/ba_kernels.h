@@ -23,16 +23,14 @@ namespace ba {
 
 /* one input (device_t) as K1 sees it for one launch */
 struct K1Device {
-    const unsigned char* iq; /* first byte of frame 0 of this launch (device memory) */
-    const unsigned char* lo; /* [lo, hi): bytes that may be touched by 16-byte vector loads */
-    const unsigned char* hi;
+    const unsigned char* iq; /* first byte of frame 0 of this launch (device memory; its allocation is 16-byte aligned and padded) */
     uint32_t hop_bytes;      /* bps, boondock_airband.cpp:418 */
     uint32_t n_frames;       /* frames in this launch */
     uint64_t frame0;         /* stream index of frame 0 */
-    float2* picks;           /* [ring_len][c_pad]: fftout[bins[c]] per frame, ring over frames */
-    float* mags;             /* [ring_len][c_pad]: |fftout[bins[c]]| = wavein[] as the bin pick writes it (.cpp:507-513) */
+    float2* picks;           /* [channel][ring_len]: fftout[bins[c]] per frame, ring over frames; NULL when no channel of the input needs raw IQ */
+    float* mags;             /* [channel][ring_len]: |fftout[bins[c]]| = wavein[] as the bin pick writes it (.cpp:507-513) */
     uint32_t ring_mask;      /* ring_len - 1 */
-    uint32_t c_pad;
+    uint32_t pad0;
     uint32_t n_channels;
     uint32_t tile0;          /* first tile index of this device in the launch-wide tile list */
     const uint32_t* bins;    /* device-resident dev->bins[] (AFC may move them between launches) */
@@ -52,10 +50,11 @@ struct K1Params {
     const float2* twiddle; /* [N], exp(-2 pi i n / N), rounded from double */
     int32_t raw_bytes;     /* shared-memory bytes reserved for the staged byte span of one tile (multiple of 16) */
     int32_t max_channels;  /* largest channel_count of any input (pick table size) */
+    uint32_t* tile_counter; /* zeroed before the launch; CTAs take tile indices from it */
 };
 
-/* returns 0 or a cudaError_t */
-int k1_launch(int fft_size, const K1Params& p, int n_ctas, cudaStream_t s);
+/* returns 0 or a cudaError_t; dbg selects the instantiation that also serves dbg_in / dbg_out / spectrum */
+int k1_launch(int fft_size, const K1Params& p, int n_ctas, bool dbg, cudaStream_t s);
 int k1_smem_bytes(int fft_size, int raw_bytes, int max_channels);
 int k1_threads(int fft_size);
 int k1_groups(int fft_size); /* FFTs a CTA works on at a time */
@@ -76,9 +75,9 @@ struct K2Ctcss {
 struct K2Chan {
     int32_t dev;          /* input index (K2Dyn) */
     uint32_t col;         /* channel index within its input = column of the pick row */
-    const float2* picks;  /* its input's pick ring */
-    const float* mags;    /* magnitudes of the same picks */
-    uint32_t ring_mask, c_pad;
+    const float2* picks;  /* this channel's row of its input's pick ring, [ring_len] (NULL when the input keeps no picks) */
+    const float* mags;    /* this channel's row of magnitudes, [ring_len] */
+    uint32_t ring_mask, pad0;
     uint32_t* bin;        /* &bins[col] (AFC moves it) */
     uint32_t base_bin;
     int32_t fft_size;
@@ -98,7 +97,8 @@ struct K2Chan {
 };
 
 /* mutable state of one channel, resident in HBM between launches */
-struct K2State {
+struct alignas(16) K2State {
+    float waveout_tail[BA_E];  /* waveout[B..B+E) kept by output_thread for the next batch (output.cpp:948); first: moved in 16-byte pieces */
     /* Squelch */
     float noise, cap, pre_full, pre_cap, post_full, post_cap;
     int32_t post_active, next, cur, delay, low_run;
@@ -116,7 +116,6 @@ struct K2State {
     float lxr0, lxr1, lxr2, lxi0, lxi1, lxi2, lyr0, lyr1, lyr2, lyi0, lyi1, lyi2;
     float ring[BA_SQ_RING];    /* Squelch::buffer_ */
     float wavein_hist[BA_E];   /* wavein[] as the loop left it for the last E frames (.cpp:548 overwrites it) */
-    float waveout_tail[BA_E];  /* waveout[B..B+E) kept by output_thread for the next batch (output.cpp:948) */
 };
 
 /* per input, per launch */
@@ -139,11 +138,13 @@ struct K2Params {
     const K2Dyn* dyn;     /* [n inputs] */
     const int32_t* order; /* channel indices in launch order (grouped by kind so that warps stay convergent) */
     int32_t n_channels;
-    int32_t wave_batch;   /* B */
+    int32_t wave_batch;   /* B, a multiple of 4 */
     const float* sincos;  /* [2][257] sin then cos, util.cpp:103-110 */
+    int32_t first_slot, end_slot; /* filled by k2_launch: the slots of `order` this kernel covers */
 };
 
-int k2_launch(const K2Params& p, cudaStream_t s);
+/* n_plain: the first n_plain slots of `order` are plain AM channels (demod_plain_kernel), the rest is general */
+int k2_launch(const K2Params& p, int n_plain, cudaStream_t s);
 
 }  // namespace ba
 #endif

@@ -7,17 +7,18 @@
  *   bin pick                                    boondock_airband.cpp:507-513            (the magnitude is taken in K2)
  *
  * Shape of the kernel
- *   - persistent CTAs walk a list of tiles; a tile = `tile_frames` consecutive frames of one input;
- *   - the byte span of the tile (frames overlap by fft_size - hop samples) is staged once in shared memory with
- *     16-byte coalesced loads, so every input byte is read from HBM/L2 once per tile;
+ *   - persistent CTAs pull tiles from a launch-wide counter; a tile = `tile_frames` consecutive frames of one input;
+ *   - the byte span of the tile (frames overlap by fft_size - hop samples) is brought into shared memory by ONE bulk
+ *     copy (cp.async.bulk -> UBLKCP, completion on an mbarrier) into the idle half of a double buffer while the FFT groups
+ *     work on the other half: every input byte is read from HBM/L2 once per tile and no thread waits on a global load;
  *   - an FFT is done by a group of G = N/16 threads (one warp for N = 512; a half warp for 256; 2..16 warps above),
  *     16 complex values per thread per pass, mixed radix 2/4/8/16 decimation in frequency, 2..4 passes;
  *     window values and twiddles of a thread do not depend on the frame, they live in registers;
  *   - between passes the data goes through a per-group shared-memory buffer whose layouts are padded/skewed so that
  *     every 8-byte load and store of a half warp hits 16 distinct bank pairs;
  *   - the last pass leaves the spectrum in a digit-reversed order; only the configured bins are read out
- *     (pick table built per input) and written as one contiguous row picks[frame][channel].
- * Sample conversion is exact: u8 levels (i - 127.5f) / 127.5f are reproduced with a Newton-corrected reciprocal
+ *     (pick table built per input) and written transposed, picks[channel][frame ring] / mags[channel][frame ring].
+ * Sample conversion is exact: u8 levels (i - 127.5f) / 127.5f are reproduced with a two-float reciprocal
  * (verified for all 256 codes by tests), products use round-to-nearest multiplies that are never contracted.
  * No cuFFT, no tensor cores: the work is FP32 butterflies and shared-memory transposes.
  */
@@ -172,13 +173,17 @@ __device__ __forceinline__ void group_sync(int grp) {
     }
 }
 
-/* exact (i - 127.5f) / 127.5f for a byte code, boondock_airband.cpp:341-343 */
-__device__ __forceinline__ float level_u8(unsigned v) {
-    const float a = __fadd_rn(__uint_as_float(0x4A800000u | (v << 1)), -4194431.5f); /* v - 127.5, exact */
-    const float r = 1.0f / 127.5f;
-    const float q = __fmul_rn(a, r);
-    const float e = __fmaf_rn(-q, 127.5f, a);
-    return __fmaf_rn(e, r, q);
+/* exact (i - 127.5f) / 127.5f for the byte `which` (0..3) of `word`, boondock_airband.cpp:341-343.
+ * PRMT drops the byte into mantissa bits 8..15 of 2^15, i.e. the float 32768 + v; v - 127.5 is then one exact subtraction.
+ * The quotient a / 127.5 is a * (r_hi + r_lo) with the reciprocal split in two floats: fma(a, r_hi, RN(a * r_lo)) equals the
+ * correctly rounded quotient for all 256 codes (checked exhaustively by tests/test_gpu_parity.py::test_u8_all_codes and,
+ * in exact rational arithmetic, by tests/test_oracle_pins.py::test_u8_level_formula). */
+template <int WHICH>
+__device__ __forceinline__ float level_u8(unsigned word) {
+    const float f = __uint_as_float(__byte_perm(word, 0x47000000u, 0x7604u | (WHICH << 4)));
+    const float a = __fadd_rn(f, -32895.5f); /* v - 127.5, exact */
+    const float r_hi = 0x1.010102p-7f, r_lo = -0x1.fdfdfep-32f;
+    return __fmaf_rn(a, r_hi, __fmul_rn(a, r_lo));
 }
 /* i / 128.0f, boondock_airband.cpp:344-346 (code 0x80 is left undefined by the reference; -1.0 here) */
 __device__ __forceinline__ float level_s8(unsigned v) {
@@ -187,11 +192,12 @@ __device__ __forceinline__ float level_s8(unsigned v) {
 
 template <int N, int FMT>
 __device__ __forceinline__ float2 load_sample(const unsigned char* frame, int n, float w, float scale) {
-    if (FMT == BA_SFMT_U8 || FMT == BA_SFMT_S8) {
+    if (FMT == BA_SFMT_U8) {
         const unsigned v = *reinterpret_cast<const unsigned short*>(frame + 2 * n);
-        const float i = (FMT == BA_SFMT_U8) ? level_u8(v & 0xffu) : level_s8(v & 0xffu);
-        const float q = (FMT == BA_SFMT_U8) ? level_u8(v >> 8) : level_s8(v >> 8);
-        return make_float2(__fmul_rn(i, w), __fmul_rn(q, w));
+        return make_float2(__fmul_rn(level_u8<0>(v), w), __fmul_rn(level_u8<1>(v), w));
+    } else if (FMT == BA_SFMT_S8) {
+        const unsigned v = *reinterpret_cast<const unsigned short*>(frame + 2 * n);
+        return make_float2(__fmul_rn(level_s8(v & 0xffu), w), __fmul_rn(level_s8(v >> 8), w));
     } else if (FMT == BA_SFMT_S16) {
         const short2 v = *reinterpret_cast<const short2*>(frame + 4 * n);
         return make_float2(__fmul_rn(__fmul_rn(scale, (float)v.x), w), __fmul_rn(__fmul_rn(scale, (float)v.y), w));
@@ -275,49 +281,74 @@ __device__ __forceinline__ void fft_pass(const ThreadConst<N>& tc, float2* __res
         fft_pass<N, FMT, PASS + 1>(tc, work, frame, scale, t, grp, dbg_in);
 }
 
-template <int N, int FMT>
-__device__ __forceinline__ void run_tile_frames(const ThreadConst<N>& tc, const K1Device& d, const unsigned char* raw0, float2* work,
+/* what the frame loop needs of a K1Device, read once per tile into registers */
+struct TileCtx {
+    unsigned hop_bytes, n_frames, ring_mask, ring_len, n_channels;
+    unsigned long long frame0;
+    float2* picks;
+    float* mags;
+    float scale;
+};
+
+template <int N, int FMT, bool DBG>
+__device__ __forceinline__ void run_tile_frames(const ThreadConst<N>& tc, const TileCtx& c, const K1Device* dg, const unsigned char* raw0, float2* work,
                                                 const uint16_t* picktab, int f0, int nf, int t, int grp) {
     using GE = Geo<N>;
-    constexpr int BYTES = (FMT == BA_SFMT_U8 || FMT == BA_SFMT_S8) ? 2 : (FMT == BA_SFMT_S16 ? 4 : 8);
-    (void)BYTES;
     for (int base = 0; base < nf; base += GE::W) {
         const bool live = base + grp < nf;
+        if (GE::G == 32 && !live)
+            break; /* a group that is exactly one warp synchronises with nobody else */
         const int fi = live ? base + grp : nf - 1; /* idle groups redo the last frame so that barriers stay uniform */
-        const unsigned char* frame = raw0 + (size_t)fi * d.hop_bytes;
+        const unsigned char* frame = raw0 + (size_t)fi * c.hop_bytes;
         const int f = f0 + fi;
-        float2* dbg_in = (live && d.dbg_in) ? d.dbg_in + (size_t)f * N : nullptr;
-        fft_pass<N, FMT, 1>(tc, work, frame, d.scale, t, grp, dbg_in);
+        float2* dbg_in = nullptr;
+        if (DBG) {
+            float2* di = dg->dbg_in;
+            dbg_in = (live && di) ? di + (size_t)f * N : nullptr;
+        }
+        fft_pass<N, FMT, 1>(tc, work, frame, c.scale, t, grp, dbg_in);
         if (live) {
-            const uint64_t fs = d.frame0 + (uint64_t)f;
-            float2* row = d.picks + (size_t)(fs & d.ring_mask) * d.c_pad;
-            float* mrow = d.mags + (size_t)(fs & d.ring_mask) * d.c_pad;
-            for (int c = t; c < (int)d.n_channels; c += GE::G) {
-                const float2 v = work[picktab[c]];
-                row[c] = v;
+            /* picked bins go out transposed, [channel][frame ring], so that the demodulator streams each channel contiguously */
+            const unsigned pos = (unsigned)((c.frame0 + (unsigned long long)f) & c.ring_mask);
+            for (int ch = t; ch < (int)c.n_channels; ch += GE::G) {
+                const float2 v = work[picktab[ch]];
+                const size_t at = (size_t)ch * c.ring_len + pos;
+                if (c.picks)
+                    c.picks[at] = v;
                 /* wavein[] = sqrtf(re*re + im*im), boondock_airband.cpp:507-513: three separately rounded operations and an IEEE square root */
-                mrow[c] = __fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)));
+                c.mags[at] = __fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)));
             }
-            if (d.dbg_out) {
-                float2* o = d.dbg_out + (size_t)f * N;
-                for (int k = t; k < N; k += GE::G)
-                    o[k] = work[GE::out_pos(k)];
-            }
-            if (d.spectrum && f == (int)d.n_frames - 1) {
-                for (int k = t; k < N; k += GE::G)
-                    d.spectrum[k] = work[GE::out_pos(k)];
+            if (DBG) {
+                float2* dout = dg->dbg_out;
+                float2* spec = dg->spectrum;
+                if (dout) {
+                    float2* o = dout + (size_t)f * N;
+                    for (int k = t; k < N; k += GE::G)
+                        o[k] = work[GE::out_pos(k)];
+                }
+                if (spec && f == (int)c.n_frames - 1) {
+                    for (int k = t; k < N; k += GE::G)
+                        spec[k] = work[GE::out_pos(k)];
+                }
             }
         }
     }
 }
 
-template <int N>
-__global__ void __launch_bounds__(Geo<N>::THREADS) channelize_kernel(K1Params p) {
+/* Persistent CTAs pull tiles from a launch-wide counter; the byte span of the next tile is fetched by one bulk copy
+ * (cp.async.bulk, completion on an mbarrier) into the other half of a double buffer while the FFT groups work on this one. */
+/* 112 registers: two CTAs of 256 threads leave 8192 registers per SM for the demodulator's warps, which run beside this kernel */
+template <int N, bool DBG>
+__global__ void __maxnreg__(112) channelize_kernel(K1Params p) {
     using GE = Geo<N>;
     BA_SHARED(smem);
-    unsigned char* raw = smem;
-    float2* work_all = reinterpret_cast<float2*>(smem + p.raw_bytes);
+    float2* work_all = reinterpret_cast<float2*>(smem + 2 * (size_t)p.raw_bytes);
     uint16_t* picktab = reinterpret_cast<uint16_t*>(work_all + GE::W * GE::WORK);
+    unsigned char* tail = reinterpret_cast<unsigned char*>(picktab + ((p.max_channels + 7) & ~7));
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(tail); /* [2] */
+    int* s_tile = reinterpret_cast<int*>(tail + 16);                        /* [2] tile index staged in each half */
+    int* s_dev = s_tile + 2;                                                /* [2] its input */
+    int* s_pre = s_dev + 2;                                                 /* [2] bytes between the 16-byte aligned copy start and frame 0 of the tile */
     const int tid = threadIdx.x;
     const int grp = tid / GE::G, t = tid % GE::G;
     float2* work = work_all + grp * GE::WORK;
@@ -337,10 +368,13 @@ __global__ void __launch_bounds__(Geo<N>::THREADS) channelize_kernel(K1Params p)
         twiddle_setup<N, 1>(tc, p.twiddle, t);
     }
 
-    int cur_dev = -1;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        /* input that owns this tile: last device with tile0 <= tile */
-        int lo = 0, hi = p.n_dev - 1;
+    /* thread 0: take the next tile off the counter and start the copy of its bytes into half `half` */
+    auto fetch = [&](int half) {
+        const int tile = (int)atomicAdd(p.tile_counter, 1u);
+        s_tile[half] = tile;
+        if (tile >= p.n_tiles)
+            return;
+        int lo = 0, hi = p.n_dev - 1; /* input that owns this tile: last device with tile0 <= tile */
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
             if (p.dev[mid].tile0 <= (uint32_t)tile)
@@ -354,63 +388,97 @@ __global__ void __launch_bounds__(Geo<N>::THREADS) channelize_kernel(K1Params p)
         const int bytes_per = (d.fmt == BA_SFMT_S16) ? 4 : (d.fmt == BA_SFMT_F32 ? 8 : 2);
         const unsigned char* g0 = d.iq + (size_t)f0 * d.hop_bytes;
         const size_t span = (size_t)(nf - 1) * d.hop_bytes + (size_t)N * bytes_per;
+        /* the copy covers whole 16-byte granules; the granules of the first and last byte of the span lie inside the
+         * stream's allocation because device allocations are at least 16-byte aligned and padded */
         const uintptr_t a0 = reinterpret_cast<uintptr_t>(g0) & ~(uintptr_t)15;
         const int pre = (int)(reinterpret_cast<uintptr_t>(g0) - a0);
-        const int chunks = (int)((pre + span + 15) >> 4);
+        const unsigned bytes = (unsigned)((pre + span + 15) & ~(size_t)15);
+        s_dev[half] = lo;
+        s_pre[half] = pre;
+        BA_MBAR_EXPECT_TX(&mbar[half], bytes);
+        BA_BULK_G2S(smem + (size_t)half * p.raw_bytes, reinterpret_cast<const void*>(a0), bytes, &mbar[half]);
+    };
 
-        __syncthreads(); /* the previous tile's frames are done with raw[] and picktab[] */
-        for (int i = tid; i < chunks; i += GE::THREADS) {
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(a0) + 16 * (size_t)i;
-            uint4 v;
-            if (src >= d.lo && src + 16 <= d.hi) {
-                v = __ldg(reinterpret_cast<const uint4*>(src));
-            } else {
-                unsigned char tmp[16];
-#pragma unroll
-                for (int b = 0; b < 16; b++)
-                    tmp[b] = (src + b >= d.lo && src + b < d.hi) ? src[b] : 0;
-                v = *reinterpret_cast<uint4*>(tmp);
-            }
-            reinterpret_cast<uint4*>(raw)[i] = v;
-        }
-        if (lo != cur_dev) {
-            for (int c = tid; c < (int)d.n_channels; c += GE::THREADS)
-                picktab[c] = (uint16_t)GE::out_pos((int)(d.bins[c] & (N - 1)));
-            cur_dev = lo;
-        }
-        __syncthreads();
+    if (tid == 0) {
+        BA_MBAR_INIT(&mbar[0], 1);
+        BA_MBAR_INIT(&mbar[1], 1);
+        BA_FENCE_MBAR_INIT();
+        fetch(0);
+    }
+    __syncthreads();
 
-        const unsigned char* raw0 = raw + pre;
-        switch (d.fmt) {
+    int half = 0, cur_dev = -1;
+    unsigned parity = 0u; /* bit h = phase parity the next wait on mbar[h] looks for */
+    for (;;) {
+        const int tile = s_tile[half];
+        if (tile >= p.n_tiles)
+            break;
+        if (tid == 0)
+            fetch(half ^ 1); /* that half was last read before the barrier that ended the previous tile */
+        const int di = s_dev[half];
+        const K1Device* dg = p.dev + di;
+        TileCtx c;
+        c.hop_bytes = dg->hop_bytes;
+        c.n_frames = dg->n_frames;
+        c.ring_mask = dg->ring_mask;
+        c.ring_len = dg->ring_mask + 1;
+        c.n_channels = dg->n_channels;
+        c.frame0 = dg->frame0;
+        c.picks = dg->picks;
+        c.mags = dg->mags;
+        c.scale = dg->scale;
+        const int fmt = dg->fmt;
+        const int f0 = (tile - (int)dg->tile0) * p.tile_frames;
+        const int nf = min(p.tile_frames, (int)c.n_frames - f0);
+        if (di != cur_dev) {
+            const uint32_t* bins = dg->bins;
+            for (int ch = tid; ch < (int)c.n_channels; ch += GE::THREADS)
+                picktab[ch] = (uint16_t)GE::out_pos((int)(bins[ch] & (N - 1)));
+            cur_dev = di;
+        }
+        BA_MBAR_WAIT(&mbar[half], (parity >> half) & 1u);
+        parity ^= 1u << half;
+        __syncthreads(); /* picktab is complete; (emulation: thread 0's copy has happened) */
+
+        const unsigned char* raw0 = smem + (size_t)half * p.raw_bytes + s_pre[half];
+        switch (fmt) {
             case BA_SFMT_U8:
-                run_tile_frames<N, BA_SFMT_U8>(tc, d, raw0, work, picktab, f0, nf, t, grp);
+                run_tile_frames<N, BA_SFMT_U8, DBG>(tc, c, dg, raw0, work, picktab, f0, nf, t, grp);
                 break;
             case BA_SFMT_S8:
-                run_tile_frames<N, BA_SFMT_S8>(tc, d, raw0, work, picktab, f0, nf, t, grp);
+                run_tile_frames<N, BA_SFMT_S8, DBG>(tc, c, dg, raw0, work, picktab, f0, nf, t, grp);
                 break;
             case BA_SFMT_S16:
-                run_tile_frames<N, BA_SFMT_S16>(tc, d, raw0, work, picktab, f0, nf, t, grp);
+                run_tile_frames<N, BA_SFMT_S16, DBG>(tc, c, dg, raw0, work, picktab, f0, nf, t, grp);
                 break;
             default:
-                run_tile_frames<N, BA_SFMT_F32>(tc, d, raw0, work, picktab, f0, nf, t, grp);
+                run_tile_frames<N, BA_SFMT_F32, DBG>(tc, c, dg, raw0, work, picktab, f0, nf, t, grp);
                 break;
         }
+        __syncthreads(); /* every group is done with this half, with picktab and with s_tile/s_dev/s_pre of this half */
+        half ^= 1;
     }
 }
 
-template <int N>
+template <int N, bool DBG>
 int launch_n(const K1Params& p, int n_ctas, cudaStream_t s) {
     using GE = Geo<N>;
-    const size_t smem = (size_t)p.raw_bytes + sizeof(float2) * GE::W * GE::WORK + sizeof(uint16_t) * ((p.max_channels + 7) & ~7);
+    const size_t smem = (size_t)k1_smem_bytes(N, p.raw_bytes, p.max_channels);
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(channelize_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(channelize_kernel<N, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess)
             return (int)e;
         configured = smem;
     }
-    BA_LAUNCH(channelize_kernel<N>, n_ctas, GE::THREADS, smem, s, p);
+    auto kern = channelize_kernel<N, DBG>;
+    BA_LAUNCH(kern, n_ctas, GE::THREADS, smem, s, p);
     return (int)cudaGetLastError();
+}
+
+template <int N>
+int launch_dbg(const K1Params& p, int n_ctas, bool dbg, cudaStream_t s) {
+    return dbg ? launch_n<N, true>(p, n_ctas, s) : launch_n<N, false>(p, n_ctas, s);
 }
 
 }  // namespace
@@ -421,24 +489,25 @@ int k1_threads(int n) {
 int k1_groups(int n) {
     return k1_threads(n) / (n / 16);
 }
+/* two halves of raw bytes, the FFT work buffers, the pick table, two mbarriers and the tile bookkeeping */
 int k1_smem_bytes(int n, int raw_bytes, int max_channels) {
-    return raw_bytes + 8 * k1_groups(n) * (n + n / 8) + 2 * ((max_channels + 7) & ~7);
+    return 2 * raw_bytes + 8 * k1_groups(n) * (n + n / 8) + 2 * ((max_channels + 7) & ~7) + 64;
 }
 
-int k1_launch(int fft_size, const K1Params& p, int n_ctas, cudaStream_t s) {
+int k1_launch(int fft_size, const K1Params& p, int n_ctas, bool dbg, cudaStream_t s) {
     switch (fft_size) {
         case 256:
-            return launch_n<256>(p, n_ctas, s);
+            return launch_dbg<256>(p, n_ctas, dbg, s);
         case 512:
-            return launch_n<512>(p, n_ctas, s);
+            return launch_dbg<512>(p, n_ctas, dbg, s);
         case 1024:
-            return launch_n<1024>(p, n_ctas, s);
+            return launch_dbg<1024>(p, n_ctas, dbg, s);
         case 2048:
-            return launch_n<2048>(p, n_ctas, s);
+            return launch_dbg<2048>(p, n_ctas, dbg, s);
         case 4096:
-            return launch_n<4096>(p, n_ctas, s);
+            return launch_dbg<4096>(p, n_ctas, dbg, s);
         case 8192:
-            return launch_n<8192>(p, n_ctas, s);
+            return launch_dbg<8192>(p, n_ctas, dbg, s);
     }
     return (int)cudaErrorInvalidValue;
 }

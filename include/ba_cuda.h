@@ -60,6 +60,8 @@ enum { BA_SQ_CLOSED = 0, BA_SQ_OPENING = 1, BA_SQ_CLOSING = 2, BA_SQ_LOW_SIGNAL_
 
 /* engine flags */
 #define BA_FLAG_TRACE 0x1u /* also return the per-sample squelch decision trace (like -DDEBUG_SQUELCH, squelch.cpp:520-633) */
+#define BA_FLAG_KEEP_PICKS 0x2u /* keep the picked-bin IQ of every channel on the device (ba_cuda_debug_picks); without it only
+                                 * inputs with a channel that needs raw IQ (NFM, bandwidth, iq outputs) keep it, plain AM needs |X| only */
 
 /* trace byte layout: bits 0-2 Squelch current_state_, bit 3 is_open(), bit 4 should_process_audio(),
  * bit 5 should_filter_sample() && needs_raw_iq (the sample went through derotation/LPF) */
@@ -188,8 +190,10 @@ BA_API int ba_cuda_commit(ba_engine* e, int dev, size_t bytes);
  * The memory must stay valid and unchanged until the ticket that consumed it has been collected. */
 BA_API int ba_cuda_submit_external(ba_engine* e, int dev, const void* iq, size_t bytes);
 
-/* Device-resident input (benchmarks, GPUDirect producers): the stream lives in HBM at d_iq;
- * ba_cuda_advance_device_stream() says how many more bytes of it are valid. */
+/* Device-resident input (benchmarks, GPUDirect producers): the stream lives in HBM at d_iq (16-byte aligned, as every
+ * device allocation is; the channelizer fetches whole 16-byte granules, so the allocation must extend to the next
+ * multiple of 16 past capacity_bytes, which cudaMalloc guarantees); ba_cuda_advance_device_stream() says how many more
+ * bytes of it are valid. */
 BA_API int ba_cuda_attach_device_stream(ba_engine* e, int dev, const void* d_iq, size_t capacity_bytes);
 BA_API int ba_cuda_advance_device_stream(ba_engine* e, int dev, size_t bytes);
 
@@ -223,7 +227,7 @@ BA_API int ba_cuda_window(ba_engine* e, float* out, size_t count);
  * (fftin, [n_frames][fft_size][2]) and/or full spectra (fftout, same shape).  Either output may be NULL. */
 BA_API int ba_cuda_debug_frames(ba_engine* e, int dev, const void* iq, size_t bytes, int n_frames, float* fftin, float* fftout);
 /* Copy out the picked-bin IQ series the last finished ticket consumed for one channel:
- * frames [first, first+count) of the device's stream, as (re,im) pairs. */
+ * frames [first, first+count) of the device's stream, as (re,im) pairs.  Needs BA_FLAG_KEEP_PICKS (or a raw-IQ channel). */
 BA_API int ba_cuda_debug_picks(ba_engine* e, int dev, int channel, uint64_t first, int count, float* out);
 /* Parity hook: append `n_frames` rows of externally computed picked-bin IQ ([n_frames][channel_count][2] floats) to the
  * device's pick ring as if the channelizer had produced them; the next ba_cuda_process() demodulates them.  Lets the

@@ -31,6 +31,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __align__(n) alignas(n)
 #define __constant__ static
 

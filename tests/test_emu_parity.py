@@ -54,6 +54,13 @@ def test_emu_cfg1_fast_path(emu):
     assert float(np.abs(res[0]["waveout"]).max()) > 0.05
 
 
+def test_emu_plain_kernel_exact(emu):
+    """demod_plain_kernel fed with the oracle's picks: audio, levels and counters bit-exact (ragged frame counts per call)."""
+    cfg, streams = scenarios.cfg1_short(0.9)
+    cfg.flags = 0
+    parity.check_demod_exact(cfg, streams, emu, frames_per_call=1777)
+
+
 def test_emu_cfg2(emu):
     cfg, streams = scenarios.cfg2_small(6, 1.1)
     o, res, _ = parity.run_both(cfg, streams, emu, chunk_bytes=1_000_003)

@@ -88,6 +88,13 @@ def test_fast_path_bit_exact(cuda):
         assert np.array_equal(got[c].view(np.uint32), o.waveout(0, c).view(np.uint32)), c
 
 
+def test_plain_kernel_exact(cuda):
+    """demod_plain_kernel fed with the oracle's picks: audio, levels and counters bit-exact (ragged frame counts per call)."""
+    cfg, streams = scenarios.cfg1_short(2.1)
+    cfg.flags = 0
+    parity.check_demod_exact(cfg, streams, cuda, frames_per_call=2777)
+
+
 def test_cfg1_picks(cuda):
     cfg, streams = scenarios.cfg1_short(0.4)
     parity.check_picks(cfg, streams[0][:2_000_000], cuda)
