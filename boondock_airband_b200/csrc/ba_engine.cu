@@ -29,6 +29,7 @@
 #include "host_model.h"
 
 #define BA_MIN_BUF_SIZE 2560000 /* MIN_BUF_SIZE, boondock_airband.h:64 */
+#define BA_SLOTS 3               /* tickets that may be outstanding: copies in, kernels and copies out of three passes overlap */
 
 namespace {
 
@@ -148,7 +149,7 @@ struct ba_engine {
     int n_plain = 0; /* slots [0, n_plain) of the launch order are plain AM channels */
     std::vector<ba::K2Chan> h_chan;
     std::vector<ba_channel_info> info;
-    Slot slot[2];
+    Slot slot[BA_SLOTS];
     int next_ticket = 0;
     uint64_t launches = 0;
     int tile_frames = 0, raw_bytes = 0, k1_ctas_per_sm = 2;
@@ -745,17 +746,24 @@ int ba_cuda_process(ba_engine* e) {
     if (!e)
         return fail(BA_ERR_BAD_ARG, "null engine");
     const int ticket = e->next_ticket;
-    Slot& s = e->slot[ticket & 1];
+    Slot& s = e->slot[ticket % BA_SLOTS];
     if (s.busy) {
         /* the slot's previous ticket was never collected: its results are about to be replaced */
         CU(cudaEventSynchronize(s.ev_done));
         s.busy = false;
     }
     if (s.used) {
-        /* this slot last served ticket-2: the input half-buffers and descriptors it read are rewritten below (wait for its
-         * kernels), its output arena is rewritten by this ticket's demodulator (wait for its device->host copies) */
+        /* this slot last served ticket - BA_SLOTS: the descriptors its kernels read are rewritten below, its output arena is
+         * rewritten by this ticket's demodulator (wait for its device->host copies) */
         CU(cudaStreamWaitEvent(e->s_in, s.ev_kdone, 0));
         CU(cudaStreamWaitEvent(e->any_afc ? e->s_k : e->s_k2, s.ev_done, 0));
+    }
+    if (ticket >= 2) {
+        /* ticket - 2: its channelizer read the input half-buffers that are refilled below, and its demodulator reads the
+         * stretch of the pick ring this ticket's channelizer is about to overwrite */
+        Slot& older = e->slot[(ticket - 2) % BA_SLOTS];
+        CU(cudaStreamWaitEvent(e->s_in, older.ev_k1, 0));
+        CU(cudaStreamWaitEvent(e->s_k, older.ev_kdone, 0));
     }
     const size_t nd = e->dev.size();
     const int B = e->B;
@@ -954,10 +962,9 @@ int ba_cuda_process(ba_engine* e) {
             e->launches++;
         }
         CU(cudaEventRecord(s.ev_k[4 * ph + 1], e->s_k));
-        if (k2s != e->s_k) {
-            CU(cudaEventRecord(s.ev_k1, e->s_k));
+        CU(cudaEventRecord(s.ev_k1, e->s_k));
+        if (k2s != e->s_k)
             CU(cudaStreamWaitEvent(k2s, s.ev_k1, 0));
-        }
         CU(cudaEventRecord(s.ev_k[4 * ph + 2], k2s));
         if (k2_any[ph]) {
             K2Params p;
@@ -1053,7 +1060,7 @@ static Slot* find_slot(ba_engine* e, int ticket) {
         fail(BA_ERR_BAD_ARG, "bad ticket %d", ticket);
         return nullptr;
     }
-    Slot& s = e->slot[ticket & 1];
+    Slot& s = e->slot[ticket % BA_SLOTS];
     if (s.ticket != ticket) {
         fail(BA_ERR_STATE, "ticket %d is not outstanding (slot holds %d)", ticket, s.ticket);
         return nullptr;

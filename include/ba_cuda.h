@@ -200,11 +200,12 @@ BA_API int ba_cuda_advance_device_stream(ba_engine* e, int dev, size_t bytes);
 /* One pass of the hot path over everything submitted so far, for all devices of the engine
  * (replaces the body of the while(true) loop, src/boondock_airband.cpp:383-737): host->device copy,
  * expand+window+FFT+bin pick, fused per-channel demodulation, device->host copy of the results.
- * Asynchronous; returns a ticket >= 0.  At most two tickets may be outstanding. */
+ * Asynchronous; returns a ticket >= 0.  At most three tickets may be outstanding (a fourth ba_cuda_process()
+ * first waits for the oldest one and reuses its result buffers). */
 BA_API int ba_cuda_process(ba_engine* e);
 /* Waits for `ticket` and describes what it produced for device `dev` (replaces the hand-off
  * waveavail=1 + Signal::send(), src/boondock_airband.cpp:673-679,728).  Pointers stay valid until
- * two more ba_cuda_process() calls have been made. */
+ * three more ba_cuda_process() calls have been made. */
 BA_API int ba_cuda_collect(ba_engine* e, int ticket, int dev, ba_step_out* out);
 /* Device time (ms) between the first and last GPU operation of a finished ticket. */
 BA_API int ba_cuda_ticket_ms(ba_engine* e, int ticket, float* ms);
