@@ -773,6 +773,14 @@ int ba_cuda_process(ba_engine* e) {
     /* 1. move new bytes to HBM and decide how many frames and batches every input runs */
     std::vector<size_t> ring_taken(nd, 0);
     bool any_ring = false;
+    /* host->device pieces are queued behind ALL the device->device carries of the step, so that the copy engine runs the
+     * big transfers back to back instead of alternating directions per input */
+    struct Piece {
+        unsigned char* dst;
+        const unsigned char* src;
+        size_t n;
+    };
+    std::vector<Piece> pieces;
     for (size_t di = 0; di < nd; di++) {
         Dev& d = *e->dev[di];
         const uint64_t room = frame_room(e, d);
@@ -816,16 +824,16 @@ int ba_cuda_process(ba_engine* e) {
                 size_t at = carry;
                 if (take_ring) {
                     const size_t first = std::min(take_ring, d.buf_size - d.bufs);
-                    CU(cudaMemcpyAsync(d.d_buf[nxt] + at, d.ring + d.bufs, first, cudaMemcpyHostToDevice, e->s_in));
+                    pieces.push_back(Piece{d.d_buf[nxt] + at, d.ring + d.bufs, first});
                     if (take_ring > first)
-                        CU(cudaMemcpyAsync(d.d_buf[nxt] + at + first, d.ring, take_ring - first, cudaMemcpyHostToDevice, e->s_in));
+                        pieces.push_back(Piece{d.d_buf[nxt] + at + first, d.ring, take_ring - first});
                     at += take_ring;
                     s.h2d_bytes += take_ring;
                     ring_taken[di] = take_ring;
                     any_ring = true;
                 }
                 for (const ExtChunk& c : take_ext) {
-                    CU(cudaMemcpyAsync(d.d_buf[nxt] + at, c.p, c.n, cudaMemcpyHostToDevice, e->s_in));
+                    pieces.push_back(Piece{d.d_buf[nxt] + at, c.p, c.n});
                     at += c.n;
                     s.h2d_bytes += c.n;
                 }
@@ -849,6 +857,8 @@ int ba_cuda_process(ba_engine* e) {
         d.step_batch0 = d.batches_done;
         d.step_batches = (int)nb;
     }
+    for (const Piece& pc : pieces)
+        CU(cudaMemcpyAsync(pc.dst, pc.src, pc.n, cudaMemcpyHostToDevice, e->s_in));
     if (any_ring) {
         /* the pinned rings are read by the copy engine: give the bytes back to the producers (bufs, .cpp:735) only once the copies are done */
         CU(cudaStreamSynchronize(e->s_in));
@@ -1004,7 +1014,14 @@ int ba_cuda_process(ba_engine* e) {
             }
             return BA_OK;
         };
-        if (uniform) {
+        if (uniform && nb0 == e->max_batches && !s.d_trace) {
+            /* a full step everywhere: one linear copy of the arena (the E carried-over samples per row ride along, 1 %) */
+            size_t floats = 0;
+            for (Dev* d : e->dev)
+                floats += (size_t)d->C * e->stride;
+            CU(cudaMemcpyAsync(s.h_wave, s.d_wave, sizeof(float) * floats, cudaMemcpyDeviceToHost, e->s_out));
+            s.d2h_bytes += sizeof(float) * floats;
+        } else if (uniform) {
             if (nb0 > 0) {
                 int rc = copy_rows(0, (size_t)e->total_channels, nb0);
                 if (rc != BA_OK)
