@@ -114,6 +114,7 @@ struct Slot {
     cudaEvent_t ev_begin = nullptr, ev_done = nullptr; /* first operation of the ticket / results are in pinned host memory */
     cudaEvent_t ev_in = nullptr, ev_kdone = nullptr;    /* inputs and descriptors are in HBM / kernels have finished */
     cudaEvent_t ev_k1 = nullptr;                        /* the channelizer of the last phase has finished */
+    cudaEvent_t ev_out0 = nullptr;                      /* the device->host stream starts on this ticket's results */
     bool used = false;
     std::vector<cudaEvent_t> ev_k; /* 4 per phase: before/after K1, before/after K2 */
     int phases = 0;
@@ -205,6 +206,8 @@ void free_engine(ba_engine* e) {
             cudaEventDestroy(s.ev_kdone);
         if (s.ev_k1)
             cudaEventDestroy(s.ev_k1);
+        if (s.ev_out0)
+            cudaEventDestroy(s.ev_out0);
         for (cudaEvent_t ev : s.ev_k)
             cudaEventDestroy(ev);
     }
@@ -605,8 +608,9 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
             }
             CU(cudaEventCreate(&s.ev_begin));
             CU(cudaEventCreate(&s.ev_done));
-            CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&s.ev_kdone, cudaEventDisableTiming));
+            CU(cudaEventCreate(&s.ev_in));
+            CU(cudaEventCreate(&s.ev_kdone));
+            CU(cudaEventCreate(&s.ev_out0));
             CU(cudaEventCreateWithFlags(&s.ev_k1, cudaEventDisableTiming));
             s.ev_k.resize(4 * (size_t)e->max_phases);
             for (cudaEvent_t& ev : s.ev_k)
@@ -996,6 +1000,7 @@ int ba_cuda_process(ba_engine* e) {
 
     CU(cudaEventRecord(s.ev_kdone, k2s));
     CU(cudaStreamWaitEvent(e->s_out, s.ev_kdone, 0));
+    CU(cudaEventRecord(s.ev_out0, e->s_out));
 
     /* 4. results to pinned host memory */
     {
@@ -1127,6 +1132,16 @@ int ba_cuda_kernel_ms(ba_engine* e, int ticket, float ms[2]) {
         ms[0] += a;
         ms[1] += b;
     }
+    return BA_OK;
+}
+
+int ba_cuda_copy_ms(ba_engine* e, int ticket, float ms[2]) {
+    Slot* s = find_slot(e, ticket);
+    if (!s || !ms)
+        return BA_ERR_BAD_ARG;
+    CU(cudaEventSynchronize(s->ev_done));
+    CU(cudaEventElapsedTime(&ms[0], s->ev_begin, s->ev_in));
+    CU(cudaEventElapsedTime(&ms[1], s->ev_out0, s->ev_done));
     return BA_OK;
 }
 

@@ -29,7 +29,7 @@ SYMBOLS = (
     "ba_cuda_submit", "ba_cuda_commit", "ba_cuda_submit_external", "ba_cuda_attach_device_stream",
     "ba_cuda_advance_device_stream", "ba_cuda_process", "ba_cuda_collect", "ba_cuda_ticket_ms", "ba_cuda_step_bytes",
     "ba_cuda_channel_info", "ba_cuda_window", "ba_cuda_debug_frames", "ba_cuda_debug_picks",
-    "ba_cuda_debug_inject_picks", "ba_cuda_launch_count", "ba_cuda_kernel_ms", "ba_cuda_mark", "ba_cuda_mark_ms",
+    "ba_cuda_debug_inject_picks", "ba_cuda_launch_count", "ba_cuda_kernel_ms", "ba_cuda_copy_ms", "ba_cuda_mark", "ba_cuda_mark_ms",
 )
 
 
@@ -71,6 +71,7 @@ def load_library(path: Optional[str] = None):
     L.ba_cuda_debug_inject_picks.argtypes = [vp, C.c_int, vp, C.c_int]
     L.ba_cuda_launch_count.argtypes = [vp, u64p]
     L.ba_cuda_kernel_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+    L.ba_cuda_copy_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     L.ba_cuda_mark.argtypes = [vp, C.c_int]
     L.ba_cuda_mark_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
     _LIBS[path] = L
@@ -183,6 +184,12 @@ class Engine:
         ms = C.c_float()
         self._check("ba_cuda_ticket_ms", self.L.ba_cuda_ticket_ms(self.h, ticket, C.byref(ms)))
         return ms.value
+
+    def copy_ms(self, ticket: int):
+        """(host->device ms, device->host ms) of a finished ticket."""
+        ms = (C.c_float * 2)()
+        self._check("ba_cuda_copy_ms", self.L.ba_cuda_copy_ms(self.h, ticket, ms))
+        return float(ms[0]), float(ms[1])
 
     def kernel_ms(self, ticket: int):
         ms = (C.c_float * 2)()

@@ -239,6 +239,10 @@ BA_API int ba_cuda_launch_count(ba_engine* e, uint64_t* launches);
 /* Per-kernel accumulated device time of the last finished ticket: ms[0]=channelize (K1), ms[1]=demod (K2). */
 BA_API int ba_cuda_kernel_ms(ba_engine* e, int ticket, float ms[2]);
 
+/* Copy legs of a finished ticket: ms[0] = host->device (input bytes + descriptors), ms[1] = device->host (results),
+ * each from the first to the last operation of that leg on its own stream. */
+BA_API int ba_cuda_copy_ms(ba_engine* e, int ticket, float ms[2]);
+
 #ifdef __cplusplus
 }
 #endif
