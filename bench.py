@@ -317,6 +317,13 @@ def main():
         torch.cuda.synchronize()
         h2d = d2h = 0
         pend = []
+        e2e_legs = [0.0, 0.0, 0.0, 0.0]
+
+        def e2e_note(old):
+            a, b = eng2.copy_ms(old)
+            c, d = eng2.kernel_ms(old)
+            for i, v in enumerate((a, b, c, d)):
+                e2e_legs[i] += v
 
         def e2e_steps(n, first):
             nonlocal h2d, d2h
@@ -333,16 +340,19 @@ def main():
                     got += r.n_batches
                     a, b = eng2.step_bytes(old)
                     h2d, d2h = h2d + a, d2h + b
+                    e2e_note(old)
             while pend:
                 old = pend.pop(0)
                 r = eng2.collect_raw(old, args.inputs - 1)
                 got += r.n_batches
                 a, b = eng2.step_bytes(old)
                 h2d, d2h = h2d + a, d2h + b
+                e2e_note(old)
             return got
 
         e2e_steps(W, True)
         h2d = d2h = 0
+        e2e_legs = [0.0, 0.0, 0.0, 0.0]
         barrier()
         t0 = time.perf_counter()
         got = e2e_steps(K, False)
@@ -356,7 +366,8 @@ def main():
             e2e_wall = float(tt.item())
         e2e_msps = world * K * step_samples / e2e_wall / 1e6
         e2e = {"value": e2e_msps, "unit": "Msps", "x_realtime": e2e_msps * 1e6 / FS, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
-               "ms_per_step": 1e3 * e2e_wall / K, "path": "ba_cuda_submit_external (pinned host) -> ba_cuda_process -> ba_cuda_collect"}
+               "ms_per_step": 1e3 * e2e_wall / K, "path": "ba_cuda_submit_external (pinned host) -> ba_cuda_process -> ba_cuda_collect",
+               "legs_ms_per_step": {"h2d": e2e_legs[0] / K, "d2h": e2e_legs[1] / K, "channelize(K1)": e2e_legs[2] / K, "demod(K2)": e2e_legs[3] / K}}
         eng2.close()
         # the ceiling of this leg is the host link: time one large pinned host -> device copy on the same box
         try:

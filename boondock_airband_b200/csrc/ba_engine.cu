@@ -111,6 +111,8 @@ struct Slot {
     ba_channel_status* h_status = nullptr;
     unsigned char* d_desc = nullptr;
     unsigned char* h_desc = nullptr;
+    ba::K1Carry* h_carry = nullptr; /* pinned; the carry kernel reads it in place */
+    cudaEvent_t ev_in2 = nullptr;   /* the second host->device stream has finished its share */
     cudaEvent_t ev_begin = nullptr, ev_done = nullptr; /* first operation of the ticket / results are in pinned host memory */
     cudaEvent_t ev_in = nullptr, ev_kdone = nullptr;    /* inputs and descriptors are in HBM / kernels have finished */
     cudaEvent_t ev_k1 = nullptr;                        /* the channelizer of the last phase has finished */
@@ -137,6 +139,8 @@ struct ba_engine {
     bool any_iq = false, any_afc = false;
     cudaStream_t stream = nullptr; /* = s_k: kernels; debug helpers run here */
     cudaStream_t s_in = nullptr, s_k = nullptr, s_k2 = nullptr, s_out = nullptr; /* host->device, K1, K2, device->host */
+    cudaStream_t s_in2 = nullptr; /* second host->device stream: alternate inputs, so that one copy's set-up hides behind the other's transfer */
+    int h2d_streams = 2;
     cudaEvent_t ev_tmp[2] = {nullptr, nullptr};
     float* d_window = nullptr;
     float2* d_twiddle = nullptr;
@@ -164,7 +168,7 @@ namespace {
 void free_engine(ba_engine* e) {
     if (!e)
         return;
-    for (cudaStream_t q : {e->s_in, e->s_k, e->s_k2, e->s_out})
+    for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2, e->s_out})
         if (q)
             cudaStreamSynchronize(q);
     for (Dev* d : e->dev) {
@@ -196,6 +200,10 @@ void free_engine(ba_engine* e) {
             cudaFreeHost(s.h_status);
         if (s.h_desc)
             cudaFreeHost(s.h_desc);
+        if (s.h_carry)
+            cudaFreeHost(s.h_carry);
+        if (s.ev_in2)
+            cudaEventDestroy(s.ev_in2);
         if (s.ev_begin)
             cudaEventDestroy(s.ev_begin);
         if (s.ev_done)
@@ -222,7 +230,7 @@ void free_engine(ba_engine* e) {
     cudaFree(e->d_ctcss);
     cudaFree(e->d_order);
     cudaFree(e->d_tile_counter);
-    for (cudaStream_t q : {e->s_in, e->s_k, e->s_k2, e->s_out})
+    for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2, e->s_out})
         if (q)
             cudaStreamDestroy(q);
     for (cudaEvent_t ev : e->ev_tmp)
@@ -437,6 +445,9 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
     CU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, desc->cuda_device));
     CU(cudaDeviceGetAttribute(&e->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, desc->cuda_device));
     CU(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&e->s_in2, cudaStreamNonBlocking));
+    if (const char* v = getenv("BA_CUDA_H2D_STREAMS"))
+        e->h2d_streams = atoi(v) >= 2 ? 2 : 1;
     CU(cudaStreamCreateWithFlags(&e->s_k, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->s_k2, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
@@ -611,6 +622,9 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
             CU(cudaEventCreate(&s.ev_in));
             CU(cudaEventCreate(&s.ev_kdone));
             CU(cudaEventCreate(&s.ev_out0));
+            CU(cudaEventCreateWithFlags(&s.ev_in2, cudaEventDisableTiming));
+            if (cudaHostAlloc((void**)&s.h_carry, sizeof(ba::K1Carry) * std::max<size_t>(1, nd), cudaHostAllocDefault) != cudaSuccess)
+                return fail(BA_ERR_NOMEM, "pinned carry list");
             CU(cudaEventCreateWithFlags(&s.ev_k1, cudaEventDisableTiming));
             s.ev_k.resize(4 * (size_t)e->max_phases);
             for (cudaEvent_t& ev : s.ev_k)
@@ -785,6 +799,7 @@ int ba_cuda_process(ba_engine* e) {
         size_t n;
     };
     std::vector<Piece> pieces;
+    int n_carry = 0;
     for (size_t di = 0; di < nd; di++) {
         Dev& d = *e->dev[di];
         const uint64_t room = frame_room(e, d);
@@ -824,7 +839,7 @@ int ba_cuda_process(ba_engine* e) {
             if (take_ring || !take_ext.empty()) {
                 const int nxt = d.cur ^ 1;
                 if (carry)
-                    CU(cudaMemcpyAsync(d.d_buf[nxt], d.d_buf[d.cur] + lo, carry, cudaMemcpyDeviceToDevice, e->s_in));
+                    s.h_carry[n_carry++] = K1Carry{d.d_buf[nxt], d.d_buf[d.cur] + lo, (uint32_t)carry, 0u};
                 size_t at = carry;
                 if (take_ring) {
                     const size_t first = std::min(take_ring, d.buf_size - d.bufs);
@@ -861,8 +876,25 @@ int ba_cuda_process(ba_engine* e) {
         d.step_batch0 = d.batches_done;
         d.step_batches = (int)nb;
     }
-    for (const Piece& pc : pieces)
-        CU(cudaMemcpyAsync(pc.dst, pc.src, pc.n, cudaMemcpyHostToDevice, e->s_in));
+    if (n_carry) {
+        /* one launch moves every input's tail; the list is read from pinned host memory in place */
+        int rc = k1_carry_launch(s.h_carry, n_carry, e->s_in);
+        if (rc != 0)
+            return fail(BA_ERR_CUDA, "carry launch: %s", cudaGetErrorString((cudaError_t)rc));
+        e->launches++;
+    }
+    {
+        const bool two = e->h2d_streams >= 2 && pieces.size() >= 2;
+        if (two)
+            CU(cudaStreamWaitEvent(e->s_in2, s.ev_begin, 0)); /* recorded behind every wait this ticket's input side needs */
+        size_t k = 0;
+        for (const Piece& pc : pieces)
+            CU(cudaMemcpyAsync(pc.dst, pc.src, pc.n, cudaMemcpyHostToDevice, (two && (k++ & 1)) ? e->s_in2 : e->s_in));
+        if (two) {
+            CU(cudaEventRecord(s.ev_in2, e->s_in2));
+            CU(cudaStreamWaitEvent(e->s_in, s.ev_in2, 0));
+        }
+    }
     if (any_ring) {
         /* the pinned rings are read by the copy engine: give the bytes back to the producers (bufs, .cpp:735) only once the copies are done */
         CU(cudaStreamSynchronize(e->s_in));
@@ -1161,7 +1193,7 @@ int ba_cuda_mark(ba_engine* e, int which) {
         return fail(BA_ERR_BAD_ARG, "bad mark %d", which);
     if (!e->marks[which])
         CU(cudaEventCreate(&e->marks[which]));
-    for (cudaStream_t q : {e->s_in, e->s_k, e->s_k2}) {
+    for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2}) {
         CU(cudaEventRecord(e->ev_tmp[0], q));
         CU(cudaStreamWaitEvent(e->s_out, e->ev_tmp[0], 0));
     }
@@ -1230,7 +1262,7 @@ int ba_cuda_debug_frames(ba_engine* e, int dev, const void* iq, size_t bytes, in
             return fail(BA_ERR_CUDA, "%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
         }                                                                                          \
     } while (0)
-    for (cudaStream_t q : {e->s_in, e->s_k, e->s_k2, e->s_out})
+    for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2, e->s_out})
         CUD(cudaStreamSynchronize(q));
     CUD(cudaMalloc((void**)&d_iq, bytes + 16));
     CUD(cudaMalloc((void**)&d_in, sizeof(float2) * N * n_frames));

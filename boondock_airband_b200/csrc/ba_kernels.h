@@ -53,6 +53,16 @@ struct K1Params {
     uint32_t* tile_counter; /* zeroed before the launch; CTAs take tile indices from it */
 };
 
+/* the unconsumed tail of an input's stream (less than one frame + one hop) moves from the half-buffer the last step read to
+ * the front of the one the next step reads (the mirrored tail of circbuffer_append, input-helpers.cpp:37-63, done in HBM) */
+struct K1Carry {
+    unsigned char* dst;
+    const unsigned char* src;
+    uint32_t n, pad0;
+};
+/* one launch for all inputs; `list` may live in pinned host memory (read once, n entries) */
+int k1_carry_launch(const K1Carry* list, int n, cudaStream_t s);
+
 /* returns 0 or a cudaError_t; dbg selects the instantiation that also serves dbg_in / dbg_out / spectrum */
 int k1_launch(int fft_size, const K1Params& p, int n_ctas, bool dbg, cudaStream_t s);
 int k1_smem_bytes(int fft_size, int raw_bytes, int max_channels);

@@ -483,6 +483,24 @@ int launch_dbg(const K1Params& p, int n_ctas, bool dbg, cudaStream_t s) {
 
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(128) carry_kernel(const K1Carry* list, int n) {
+    const int i = blockIdx.x;
+    if (i >= n)
+        return;
+    const K1Carry c = list[i];
+    for (uint32_t b = threadIdx.x; b < c.n; b += blockDim.x)
+        c.dst[b] = c.src[b];
+}
+}  // namespace
+
+int k1_carry_launch(const K1Carry* list, int n, cudaStream_t s) {
+    if (n <= 0)
+        return 0;
+    BA_LAUNCH(carry_kernel, n, 128, 0, s, list, n);
+    return (int)cudaGetLastError();
+}
+
 int k1_threads(int n) {
     return n >= 8192 ? 512 : 256;
 }

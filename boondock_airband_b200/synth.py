@@ -64,8 +64,9 @@ def quantise(x: np.ndarray, fmt: str) -> np.ndarray:
 
 
 def synth(dev: DeviceCfg, seconds: float, index: int = 0, gate_on: float = 1.5, gate_off: float = 0.5,
-          n_samples: Optional[int] = None, chunk: int = 1 << 18) -> np.ndarray:
-    """Interleaved IQ (dtype per dev.sample_format) for one input."""
+          n_samples: Optional[int] = None, chunk: int = 1 << 18, am_depth: float = 0.5, carrier_dbfs=None, burst: float = 1.0) -> np.ndarray:
+    """Interleaved IQ (dtype per dev.sample_format) for one input.  `am_depth`, `carrier_dbfs` (one level per
+    carrier) and `burst` (amplitude factor over the second half of every transmission) are for the stress scenarios of the parity tests (marginal carriers, AGC clipping)."""
     fs = float(dev.sample_rate)
     n = int(round(seconds * fs)) if n_samples is None else int(n_samples)
     plan = _plan(dev)
@@ -79,12 +80,17 @@ def synth(dev: DeviceCfg, seconds: float, index: int = 0, gate_on: float = 1.5, 
         t = (start + np.arange(m, dtype=np.float64)) / fs
         x = (rng.standard_normal(m, dtype=np.float32) + 1j * rng.standard_normal(m, dtype=np.float32)) * np.float32(sigma)
         x = x.astype(np.complex64)
-        am_env = (1.0 + 0.5 * np.sin(2 * np.pi * 1000.0 * t)).astype(np.float32)
+        am_env = (1.0 + am_depth * np.sin(2 * np.pi * 1000.0 * t)).astype(np.float32)
         fm_voice = 2.5 * np.sin(2 * np.pi * 1000.0 * t)
         for c, (off, kind, tone) in enumerate(plan):
-            gate = (np.mod(t + 0.1 * c, period) < gate_on)
+            if carrier_dbfs is not None:
+                amp = 10.0 ** (carrier_dbfs[c] / 20.0)
+            gate_phase = np.mod(t + 0.1 * c, period)
+            gate = (gate_phase < gate_on)
             if not gate.any():
                 continue
+            if burst != 1.0:
+                gate = gate * np.where(gate_phase >= 0.5 * gate_on, np.float32(burst), np.float32(1.0))
             ph = 2 * np.pi * off * t
             if kind == 1:
                 ph = ph + fm_voice

@@ -15,6 +15,18 @@ def cfg1_short(seconds=0.9):
     return cfg, [iq]
 
 
+def am_stress(seconds=1.5, index=11):
+    """Plain AM channels driven hard: carriers from strong to below the squelch threshold (decisions flip on noise),
+    a threefold amplitude step halfway through each transmission (the AGC clip branch, .cpp:583-586) and 130 ms transmissions 40 ms apart (flap detection,
+    low-signal aborts, every delay running out).  For the bit-exact checks of the demodulator."""
+    cfg = configs.cfg1()
+    cfg.flags = abi.FLAG_TRACE
+    cfg.max_batches_per_step = 3
+    levels = [-25.0, -35.0, -44.0, -46.0, -47.0, -48.0, -49.0, -50.0]
+    iq = synth.synth(cfg.devices[0], seconds, index, gate_on=0.13, gate_off=0.04, am_depth=0.9, carrier_dbfs=levels, burst=3.0)
+    return cfg, [iq]
+
+
 def cfg2_small(n_channels=8, seconds=1.3):
     cfg = configs.cfg2(n_channels)
     cfg.flags = abi.FLAG_TRACE

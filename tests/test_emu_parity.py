@@ -61,6 +61,14 @@ def test_emu_plain_kernel_exact(emu):
     parity.check_demod_exact(cfg, streams, emu, frames_per_call=1777)
 
 
+def test_emu_plain_kernel_stress_exact(emu):
+    """The speculative quad path of demod_plain_kernel against the sequential loop on marginal, flapping, clipping
+    carriers (every squelch state, flap detection, low-signal aborts, AGC clip): bit-exact."""
+    cfg, streams = scenarios.am_stress(1.4)
+    cfg.flags = 0
+    parity.check_demod_exact(cfg, streams, emu, frames_per_call=2333)
+
+
 def test_emu_cfg2(emu):
     cfg, streams = scenarios.cfg2_small(6, 1.1)
     o, res, _ = parity.run_both(cfg, streams, emu, chunk_bytes=1_000_003)

@@ -95,6 +95,22 @@ def test_plain_kernel_exact(cuda):
     parity.check_demod_exact(cfg, streams, cuda, frames_per_call=2777)
 
 
+@pytest.mark.parametrize("frames_per_call", [1100, 2777, 8000])
+def test_plain_kernel_stress_exact(cuda, frames_per_call):
+    """The speculative quad path of demod_plain_kernel against the sequential loop on marginal, flapping, clipping
+    carriers (every squelch state, flap detection, low-signal aborts, AGC clip): bit-exact."""
+    cfg, streams = scenarios.am_stress(3.0)
+    cfg.flags = 0
+    cfg.max_batches_per_step = 8
+    parity.check_demod_exact(cfg, streams, cuda, frames_per_call=frames_per_call)
+
+
+def test_general_kernel_stress_exact(cuda):
+    """Same stimulus through the general kernel (trace on)."""
+    cfg, streams = scenarios.am_stress(2.0)
+    parity.check_demod_exact(cfg, streams, cuda, frames_per_call=2777)
+
+
 def test_cfg1_picks(cuda):
     cfg, streams = scenarios.cfg1_short(0.4)
     parity.check_picks(cfg, streams[0][:2_000_000], cuda)
