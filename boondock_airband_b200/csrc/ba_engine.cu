@@ -139,6 +139,8 @@ struct ba_engine {
     bool any_iq = false, any_afc = false;
     cudaStream_t stream = nullptr; /* = s_k: kernels; debug helpers run here */
     cudaStream_t s_in = nullptr, s_k = nullptr, s_k2 = nullptr, s_out = nullptr; /* host->device, K1, K2, device->host */
+    cudaStream_t s_k2b = nullptr; /* the plain-AM demodulator runs here beside the general one */
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t s_in2 = nullptr; /* second host->device stream: alternate inputs, so that one copy's set-up hides behind the other's transfer */
     int h2d_streams = 2;
     cudaEvent_t ev_tmp[2] = {nullptr, nullptr};
@@ -168,7 +170,7 @@ namespace {
 void free_engine(ba_engine* e) {
     if (!e)
         return;
-    for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2, e->s_out})
+    for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2, e->s_k2b, e->s_out})
         if (q)
             cudaStreamSynchronize(q);
     for (Dev* d : e->dev) {
@@ -230,10 +232,10 @@ void free_engine(ba_engine* e) {
     cudaFree(e->d_ctcss);
     cudaFree(e->d_order);
     cudaFree(e->d_tile_counter);
-    for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2, e->s_out})
+    for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2, e->s_k2b, e->s_out})
         if (q)
             cudaStreamDestroy(q);
-    for (cudaEvent_t ev : e->ev_tmp)
+    for (cudaEvent_t ev : {e->ev_tmp[0], e->ev_tmp[1], e->ev_fork, e->ev_join})
         if (ev)
             cudaEventDestroy(ev);
     delete e;
@@ -446,6 +448,9 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
     CU(cudaDeviceGetAttribute(&e->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, desc->cuda_device));
     CU(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->s_in2, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&e->s_k2b, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     if (const char* v = getenv("BA_CUDA_H2D_STREAMS"))
         e->h2d_streams = atoi(v) >= 2 ? 2 : 1;
     CU(cudaStreamCreateWithFlags(&e->s_k, cudaStreamNonBlocking));
@@ -1021,7 +1026,7 @@ int ba_cuda_process(ba_engine* e) {
             p.n_channels = e->total_channels;
             p.wave_batch = B;
             p.sincos = e->d_sincos;
-            int rc = k2_launch(p, e->n_plain, k2s);
+            int rc = k2_launch(p, e->n_plain, k2s, e->s_k2b, e->ev_fork, e->ev_join);
             if (rc != 0)
                 return fail(BA_ERR_CUDA, "demod launch: %s", cudaGetErrorString((cudaError_t)rc));
             e->launches += (e->n_plain > 0 ? 1 : 0) + (e->total_channels > e->n_plain ? 1 : 0);
@@ -1262,7 +1267,7 @@ int ba_cuda_debug_frames(ba_engine* e, int dev, const void* iq, size_t bytes, in
             return fail(BA_ERR_CUDA, "%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
         }                                                                                          \
     } while (0)
-    for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2, e->s_out})
+    for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2, e->s_k2b, e->s_out})
         CUD(cudaStreamSynchronize(q));
     CUD(cudaMalloc((void**)&d_iq, bytes + 16));
     CUD(cudaMalloc((void**)&d_in, sizeof(float2) * N * n_frames));

@@ -153,8 +153,9 @@ struct K2Params {
     int32_t first_slot, end_slot; /* filled by k2_launch: the slots of `order` this kernel covers */
 };
 
-/* n_plain: the first n_plain slots of `order` are plain AM channels (demod_plain_kernel), the rest is general */
-int k2_launch(const K2Params& p, int n_plain, cudaStream_t s);
+/* n_plain: the first n_plain slots of `order` are plain AM channels (demod_plain_kernel), the rest is general (one warp per
+ * channel); s2/fork/join (optional) let the two kernels run concurrently */
+int k2_launch(const K2Params& p, int n_plain, cudaStream_t s, cudaStream_t s2, cudaEvent_t fork, cudaEvent_t join);
 
 }  // namespace ba
 #endif
