@@ -269,7 +269,7 @@ int setup_channel(ba_engine* e, Dev& d, int ci, ba::K2Chan& k, ba::K2State& st, 
     k.modulation = cd.modulation;
     k.afc = cd.afc & 0xff;
     k.has_iq_outputs = cd.has_iq_outputs ? 1 : 0;
-    k.needs_raw_iq = (cd.modulation == BA_MOD_NFM || cd.bandwidth > 0 || cd.has_iq_outputs) ? 1 : 0; /* config.cpp:162,596,674-680 */
+    k.needs_raw_iq = (cd.modulation == BA_MOD_NFM || cd.bandwidth != 0 || cd.has_iq_outputs) ? 1 : 0; /* config.cpp:162,596,674-680 */
     k.fm_demod = e->fm_demod;
     k.ampfactor = cd.ampfactor;
     float alpha = model::alpha_default(R);
@@ -506,7 +506,7 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
                 d->any_afc = true;
             if (c.has_iq_outputs)
                 d->any_iq = true;
-            if (c.modulation == BA_MOD_NFM || c.bandwidth > 0 || c.has_iq_outputs) /* needs_raw_iq, config.cpp:162,596,674-680 */
+            if (c.modulation == BA_MOD_NFM || c.bandwidth != 0 || c.has_iq_outputs) /* needs_raw_iq, config.cpp:162,596,674-680 */
                 d->any_raw = true;
             if (c.ctcss > 0)
                 n_ctcss++;
@@ -699,6 +699,17 @@ int ba_cuda_submit(ba_engine* e, int dev, const void* iq, size_t len) {
         memcpy(d->ring + d->buf_size, d->ring, std::min(len - space_left, d->mirror));
     }
     d->bufe = (d->bufe + len) % d->buf_size;
+    return BA_OK;
+}
+
+int ba_cuda_input_space(ba_engine* e, int dev, size_t* free_bytes) {
+    Dev* d = get_dev(e, dev);
+    if (!d || !free_bytes)
+        return fail(BA_ERR_BAD_ARG, "bad argument");
+    std::lock_guard<std::mutex> g(d->lock);
+    /* what ba_cuda_submit() accepts right now: one byte less than the unread gap (bufe may not catch up with bufs) */
+    const size_t gap = d->buf_size - ring_available(*d);
+    *free_bytes = gap > 0 ? gap - 1 : 0;
     return BA_OK;
 }
 

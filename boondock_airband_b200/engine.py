@@ -26,7 +26,7 @@ _LIBS = {}
 # every symbol include/ba_cuda.h declares
 SYMBOLS = (
     "ba_cuda_create", "ba_cuda_destroy", "ba_cuda_last_error", "ba_cuda_visible_devices", "ba_cuda_input_ring",
-    "ba_cuda_submit", "ba_cuda_commit", "ba_cuda_submit_external", "ba_cuda_attach_device_stream",
+    "ba_cuda_submit", "ba_cuda_input_space", "ba_cuda_commit", "ba_cuda_submit_external", "ba_cuda_attach_device_stream",
     "ba_cuda_advance_device_stream", "ba_cuda_process", "ba_cuda_collect", "ba_cuda_ticket_ms", "ba_cuda_step_bytes",
     "ba_cuda_channel_info", "ba_cuda_window", "ba_cuda_debug_frames", "ba_cuda_debug_picks",
     "ba_cuda_debug_inject_picks", "ba_cuda_launch_count", "ba_cuda_kernel_ms", "ba_cuda_copy_ms", "ba_cuda_mark", "ba_cuda_mark_ms",
@@ -69,6 +69,7 @@ def load_library(path: Optional[str] = None):
     L.ba_cuda_debug_frames.argtypes = [vp, C.c_int, vp, sz, C.c_int, vp, vp]
     L.ba_cuda_debug_picks.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, C.c_int, vp]
     L.ba_cuda_debug_inject_picks.argtypes = [vp, C.c_int, vp, C.c_int]
+    L.ba_cuda_input_space.argtypes = [vp, C.c_int, C.POINTER(C.c_size_t)]
     L.ba_cuda_launch_count.argtypes = [vp, u64p]
     L.ba_cuda_kernel_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     L.ba_cuda_copy_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
@@ -158,6 +159,11 @@ class Engine:
         buf, size, mirror = C.c_void_p(), C.c_size_t(), C.c_size_t()
         self._check("ba_cuda_input_ring", self.L.ba_cuda_input_ring(self.h, dev, C.byref(buf), C.byref(size), C.byref(mirror)))
         return buf.value, size.value, mirror.value
+
+    def input_space(self, dev: int) -> int:
+        n = C.c_size_t()
+        self._check("ba_cuda_input_space", self.L.ba_cuda_input_space(self.h, dev, C.byref(n)))
+        return n.value
 
     def commit(self, dev: int, nbytes: int):
         self._check("ba_cuda_commit", self.L.ba_cuda_commit(self.h, dev, nbytes))
@@ -251,7 +257,7 @@ class Engine:
         nd = len(self.cfg.devices)
         views = [np.ascontiguousarray(s).view(np.uint8).reshape(-1) for s in streams]
         pos = [0] * nd
-        acc = [dict(waveout=[], iq_out=[], trace=[], status=[], frames_done=0) for _ in range(nd)]
+        acc = self._new_acc()
         if chunk_bytes is None:
             chunk_bytes = 1 << 20
         while True:
@@ -262,25 +268,51 @@ class Engine:
                     self.submit(d, views[d][pos[d]:pos[d] + n])
                     pos[d] += n
                     fed = True
-            t = self.process()
-            produced = False
-            for d in range(nd):
-                r = self.collect(t, d)
-                acc[d]["frames_done"] = r.frames_done
-                if r.n_batches:
-                    produced = True
-                    acc[d]["waveout"].append(r.waveout)
-                    if r.iq_out is not None:
-                        acc[d]["iq_out"].append(r.iq_out)
-                    if r.trace is not None:
-                        acc[d]["trace"].append(r.trace)
-                    for b in range(r.n_batches):
-                        acc[d]["status"].append([r.status(b, c) for c in range(r.channel_count)])
+            produced, _ = self._step_into(acc)
             if not fed and not produced:
                 break
+        return self._finish_acc(acc)
+
+    def run_file_inputs(self, inputs, idle_sleep: float = 0.0002):
+        """The demodulator side of a file replay: inputs[dev] is a started host.FileInput appending to device dev's ring
+        from its own thread (file_rx_thread, input-file.cpp:82-147).  Runs until every input has hit end of file
+        (state INPUT_FAILED, as in the reference) and the rings are drained; returns what run_stream returns."""
+        import time
+        acc = self._new_acc()
+        while True:
+            ended = all(i.state in (3, 4) for i in inputs)  # INPUT_FAILED / INPUT_STOPPED, read BEFORE the pass
+            produced, advanced = self._step_into(acc)
+            if ended and not produced and not advanced:
+                break
+            if not advanced:
+                time.sleep(idle_sleep)  # demodulate() sleeps 10 ms here (boondock_airband.cpp:421-423)
+        return self._finish_acc(acc)
+
+    def _new_acc(self):
+        return [dict(waveout=[], iq_out=[], trace=[], status=[], frames_done=0) for _ in self.cfg.devices]
+
+    def _step_into(self, acc):
+        """One process() + collect() of every device; returns (some batch came out, some frame was consumed)."""
+        t = self.process()
+        produced = advanced = False
+        for d in range(len(acc)):
+            r = self.collect(t, d)
+            advanced |= r.frames_done != acc[d]["frames_done"]
+            acc[d]["frames_done"] = r.frames_done
+            if r.n_batches:
+                produced = True
+                acc[d]["waveout"].append(r.waveout)
+                if r.iq_out is not None:
+                    acc[d]["iq_out"].append(r.iq_out)
+                if r.trace is not None:
+                    acc[d]["trace"].append(r.trace)
+                for b in range(r.n_batches):
+                    acc[d]["status"].append([r.status(b, c) for c in range(r.channel_count)])
+        return produced, advanced
+
+    def _finish_acc(self, acc):
         out = []
-        for d in range(nd):
-            a = acc[d]
+        for d, a in enumerate(acc):
             c = len(self.cfg.devices[d].channels)
             out.append(dict(
                 waveout=np.concatenate(a["waveout"], axis=1) if a["waveout"] else np.zeros((c, 0), np.float32),

@@ -86,7 +86,8 @@ typedef struct ba_channel_desc {
     float notch;                   /* "notch" Hz, 0 = off (config.cpp:516-562) */
     float notch_q;                 /* "notch_q", 0 = default 10.0 */
     float ctcss;                   /* "ctcss" Hz, 0 = off (config.cpp:563-590) */
-    int32_t bandwidth;             /* "bandwidth" Hz, 0 = off; low-pass at bandwidth/2 (config.cpp:591-622) */
+    int32_t bandwidth;             /* "bandwidth" Hz, 0 = off; low-pass at bandwidth/2 (config.cpp:591-622); <0 = the key was there
+                                    * but its value was rejected: needs_raw_iq is set, no filter (config.cpp:592,609-610) */
     int32_t tau_us;                /* "tau" µs; <0 = inherit the device value (config.cpp:652-656) */
     int32_t has_iq_outputs;        /* channel_t.has_iq_outputs: a rawfile output wants iq_out (config.cpp:162) */
 } ba_channel_desc;
@@ -181,6 +182,8 @@ BA_API int ba_cuda_input_ring(ba_engine* e, int dev, unsigned char** buffer, siz
 /* Replaces circbuffer_append() for callers that do not own an input_t (src/input-helpers.cpp:37-63):
  * appends `bytes` of interleaved IQ from host memory to the device's stream.  */
 BA_API int ba_cuda_submit(ba_engine* e, int dev, const void* iq, size_t bytes);
+/* Bytes ba_cuda_submit() would accept right now (the space test of file_rx_thread, src/input-file.cpp:126-133). */
+BA_API int ba_cuda_input_space(ba_engine* e, int dev, size_t* free_bytes);
 /* Same, for callers that wrote into the ring from ba_cuda_input_ring() themselves
  * (the rx thread of an unmodified input driver): publishes `bytes` more bytes at the ring's write index. */
 BA_API int ba_cuda_commit(ba_engine* e, int dev, size_t bytes);

@@ -1,0 +1,114 @@
+/*
+ * ba_host.h — host-side pieces either side of the CUDA hot path, plain C ABI.
+ *
+ *   ba_conf_*        a reader for the subset of the libconfig grammar the reference's configuration files use and the
+ *                    translation of `devices` / `channels` into the descriptors of include/ba_cuda.h, with the rules of
+ *                    parse_devices() / parse_channels() (src/config.cpp:298-836): number forms (int Hz, float MHz, "118.5M"
+ *                    strings), defaults, validation errors, the disabled-entry skipping and the two silent channel drops.
+ *                    libconfig++ is not needed.
+ *   ba_file_input_*  the file input driver (src/input-file.cpp:35-181) with a selectable sample format and unpaced replay:
+ *                    a reader thread that appends to the input's ring with the arithmetic of circbuffer_append
+ *                    (src/input-helpers.cpp:37-63) and waits for a full ring in 20 us .. 1 ms naps instead of 10 ms per poll.
+ *
+ * Nothing here touches CUDA; libba_host.so loads on a machine without a GPU.  The engine is reached only through the
+ * function pointers of ba_ring_sink, which ba_file_input_sink_for_engine() fills from libba_cuda.so's entry points.
+ */
+#ifndef BA_HOST_H
+#define BA_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "ba_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define BA_HOST_API
+#else
+#define BA_HOST_API __attribute__((visibility("default")))
+#endif
+
+/* ---------------------------------------------------------------- configuration front-end (row f-2) */
+
+typedef struct ba_conf ba_conf;
+
+/* error codes of this library (negative), besides BA_OK */
+#define BA_HOST_ERR_SYNTAX (-20) /* the text is not in the grammar; ba_host_last_error() names line and column */
+#define BA_HOST_ERR_CONFIG (-21) /* a "Configuration error" of config.cpp (the reference prints it and calls error() = _Exit(1)) */
+#define BA_HOST_ERR_IO (-22)
+#define BA_HOST_ERR_UNSUPPORTED (-23) /* valid for the reference, outside this engine (scan mode) */
+
+/* wave_rate: 8000 = the reference built without -DNFM, 16000 = with it (boondock_airband.h:67-71); 0 = 16000 when any
+ * channel says modulation = "nfm", else 8000.  With 8000 a "nfm" channel is the reference's "unknown modulation" error. */
+BA_HOST_API int ba_conf_parse_file(const char* path, int wave_rate, ba_conf** out);
+BA_HOST_API int ba_conf_parse_text(const char* text, int wave_rate, ba_conf** out);
+BA_HOST_API void ba_conf_free(ba_conf* c);
+BA_HOST_API const char* ba_host_last_error(void);
+
+/* The engine descriptor built from `devices` (pointers stay valid until ba_conf_free).  cuda_device, flags and
+ * max_batches_per_step are left 0 for the caller to fill. */
+BA_HOST_API const ba_engine_desc* ba_conf_engine_desc(const ba_conf* c);
+BA_HOST_API int ba_conf_device_count(const ba_conf* c);
+/* Settings of the i-th enabled device the input driver reads itself: "type", "filepath", "speedup_factor", "sample_format",
+ * "index", "serial", "gain", "device_string", ...  Strings come back as written, numbers formatted with %.17g. NULL if absent. */
+BA_HOST_API const char* ba_conf_device_setting(const ba_conf* c, int device, const char* key);
+/* root-level switches demodulate()'s callers read (boondock_airband.cpp:852-893) */
+BA_HOST_API int ba_conf_multiple_demod_threads(const ba_conf* c);
+/* Warnings the reference prints to stderr while parsing (obsolete 'squelch', conflicting thresholds, frequency outside the
+ * device's bandwidth) plus a note for every silently dropped channel; '\n'-separated, "" if none. */
+BA_HOST_API const char* ba_conf_warnings(const ba_conf* c);
+/* index of the configuration's channel entry (position in the `channels` list, disabled ones counted) for channel `ch` of
+ * enabled device `device`; -1 if out of range */
+BA_HOST_API int ba_conf_channel_source_index(const ba_conf* c, int device, int ch);
+
+/* ---------------------------------------------------------------- file input (row f-1) */
+
+/* Where the reader thread puts bytes: the input_t ring (input-common.h:39-57).  `space` returns the free bytes of the
+ * ring, `append` copies n bytes in (it is only called with n <= the space last reported), both are called from the
+ * reader thread only. */
+typedef struct ba_ring_sink {
+    void* ctx;
+    size_t (*space)(void* ctx);
+    int (*append)(void* ctx, const void* data, size_t n); /* 0 or a negative BA_ERR_* */
+} ba_ring_sink;
+
+typedef struct ba_file_input_desc {
+    const char* filepath;     /* "filepath" (input-file.cpp:40-45) */
+    int32_t sample_format;    /* BA_SFMT_*; the reference's driver is BA_SFMT_U8 only (input-file.cpp:170-172) */
+    int32_t sample_rate;      /* Hz, for pacing */
+    double speedup_factor;    /* "speedup_factor": replay speed relative to real time, the reference's default is 4; 0 = unpaced */
+    size_t chunk_bytes;       /* bytes per read; 0 = half the ring minus one, as input-file.cpp:96 */
+    size_t ring_bytes;        /* size of the ring behind `sink` (for the default chunk size) */
+    int32_t loop;             /* != 0: rewind at end of file instead of stopping (benchmarks) */
+} ba_file_input_desc;
+
+typedef struct ba_file_input ba_file_input;
+
+/* input state, as input_t.state (input-common.h:33-37) */
+#define BA_INPUT_UNKNOWN 0
+#define BA_INPUT_INITIALIZED 1
+#define BA_INPUT_RUNNING 2
+#define BA_INPUT_FAILED 3
+#define BA_INPUT_STOPPED 4
+
+BA_HOST_API int ba_file_input_open(const ba_file_input_desc* desc, const ba_ring_sink* sink, ba_file_input** out); /* file_init */
+BA_HOST_API int ba_file_input_start(ba_file_input* f);                                                              /* run_rx_thread */
+BA_HOST_API int ba_file_input_state(const ba_file_input* f); /* BA_INPUT_FAILED after end of file or a read error, like the reference */
+BA_HOST_API uint64_t ba_file_input_bytes(const ba_file_input* f); /* bytes appended so far */
+BA_HOST_API int ba_file_input_stop(ba_file_input* f);              /* file_stop: joins the thread, closes the file, frees f */
+
+/* A sink that feeds input `dev` of an engine through ba_cuda_submit(); `submit` and `space` are libba_cuda.so's
+ * ba_cuda_submit and ba_cuda_input_space (passed as pointers so that this library does not link against CUDA). */
+typedef int (*ba_submit_fn)(ba_engine* e, int dev, const void* iq, size_t bytes);
+typedef int (*ba_space_fn)(ba_engine* e, int dev, size_t* free_bytes);
+BA_HOST_API int ba_file_input_sink_for_engine(ba_engine* e, int dev, ba_submit_fn submit, ba_space_fn space, ba_ring_sink* out);
+/* frees what ba_file_input_sink_for_engine() put behind out->ctx (after ba_file_input_stop) */
+BA_HOST_API void ba_file_input_sink_release(ba_ring_sink* sink);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -472,7 +472,7 @@ int fill_channel(ba_oracle* o, Device& d, Channel& c, const ba_channel_desc& cd)
     c.afc = cd.afc & 0xff;
     c.ampfactor = cd.ampfactor;
     c.has_iq_outputs = cd.has_iq_outputs ? 1 : 0;
-    c.needs_raw_iq = (cd.modulation == BA_MOD_NFM || cd.bandwidth > 0 || cd.has_iq_outputs) ? 1 : 0; /* config.cpp:162,596,674-680 */
+    c.needs_raw_iq = (cd.modulation == BA_MOD_NFM || cd.bandwidth != 0 || cd.has_iq_outputs) ? 1 : 0; /* config.cpp:162,596,674-680 */
     c.wavein.assign(2 * B + E, 0.0f);
     c.waveout.assign(2 * B + E, 0.0f);
     c.iq_in.assign(2 * (2 * B + E), 0.0f);

@@ -92,6 +92,33 @@ def run_both(cfg: abi.EngineCfg, streams, lib: str, chunk_bytes: int = 1 << 20, 
     return o, res, launches
 
 
+def run_files(conf, cfg: abi.EngineCfg, streams, lib: str, ref: bool = False, chunk_bytes: int = 0):
+    """The file replay: one host.FileInput reader thread per device (as the reference's input threads), the demodulator
+    loop on this thread.  The oracle gets the same bytes in one piece."""
+    from boondock_airband_b200 import host
+    o = Oracle(cfg, ref=ref)
+    for d, s in enumerate(streams):
+        o.feed(d, s)
+    e = Engine(cfg, lib)
+    inputs = []
+    try:
+        for d, dev in enumerate(cfg.devices):
+            assert conf.setting(d, "type") == "file"
+            inputs.append(host.FileInput(e, d, conf.setting(d, "filepath"), sample_format=dev.sample_format, sample_rate=dev.sample_rate,
+                                         speedup_factor=0.0, chunk_bytes=chunk_bytes))  # unpaced, whatever speedup_factor the file says
+        for i in inputs:
+            i.start()
+        res = e.run_file_inputs(inputs)
+        for d, i in enumerate(inputs):
+            assert i.state == host.INPUT_FAILED  # end of file disables the input, as input-file.cpp:107-111
+            assert i.bytes == np.ascontiguousarray(streams[d]).nbytes
+    finally:
+        for i in inputs:
+            i.stop()
+        e.close()
+    return o, res
+
+
 def compare_streams(cfg: abi.EngineCfg, o: Oracle, res, exact: bool = False, min_open: int = 0):
     """Squelch decisions (trace) identical; audio within TOL_AUDIO (or bit-exact); status scalars consistent."""
     report = []

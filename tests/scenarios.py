@@ -76,3 +76,38 @@ def squelch_steps(levels, fft_size=512):
     z = np.zeros((len(levels), 1, 2), np.float32)
     z[:, 0, 0] = levels
     return z
+
+
+FILE_REPLAY_CONF = """
+# two file inputs in one configuration file, as an unmodified airband .conf would name them (rows f-1 / f-2)
+fft_size = 512;
+multiple_demod_threads = false;
+devices: (
+  { type = "file"; filepath = "%(a)s"; sample_rate = 2.4; centerfreq = 145.0; sample_format = "S16"; speedup_factor = 100;
+    channels: (
+      { freq = 144.7; modulation = "nfm"; bandwidth = 12500; ctcss = 100.0; notch = 100.0; %(o)s },
+      { freq = 144.85; %(o)s },
+      { freq = 145.15; disable = true; %(o)s },
+      { freq = 145.3; modulation = "nfm"; outputs: ( { type = "rawfile"; directory = "/tmp"; filename_template = "iq"; } ); },
+      { freq = 145.45; bandwidth = "8k"; ampfactor = 1.5; squelch_snr_threshold = 6; %(o)s }
+    ); },
+  { type = "file"; filepath = "%(b)s"; sample_rate = 2560000; centerfreq = 120000000;
+    channels: ( { freq = 119.5; %(o)s }, { freq = 120.225; afc = 6; %(o)s }, { freq = 120800000; squelch_threshold = -42; %(o)s } ); }
+);
+"""
+
+
+def file_replay(tmp_path, seconds=0.6):
+    """Writes the IQ files and returns (configuration text, parsed EngineCfg, the streams as written)."""
+    from boondock_airband_b200 import host
+    out = 'outputs: ( { type = "file"; directory = "/tmp"; filename_template = "x"; } );'
+    a, b = str(tmp_path / "dev0.cs16"), str(tmp_path / "dev1.cu8")
+    text = FILE_REPLAY_CONF % {"a": a, "b": b, "o": out}
+    conf = host.parse_text(text)
+    cfg = conf.cfg
+    cfg.flags = abi.FLAG_TRACE
+    cfg.max_batches_per_step = 2
+    streams = [synth.synth(cfg.devices[0], seconds, 31, gate_on=0.25, gate_off=0.1), synth.synth(cfg.devices[1], seconds * 1.2, 32, gate_on=0.2, gate_off=0.08)]
+    for path, s in zip((a, b), streams):
+        s.tofile(path)
+    return conf, cfg, streams

@@ -99,7 +99,7 @@ def test_product_never_touches_the_oracle():
                 text = open(path).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), path
                 assert "libba_oracle" not in text and "TESTONLY" not in text, path
-            elif f.endswith((".cu", ".h", "Makefile")):
+            elif f.endswith((".cu", ".cpp", ".h", "Makefile")):
                 text = open(path).read()
                 assert not re.search(r'#include\s+"[^"]*oracle', text), path
                 assert "libba_oracle" not in text and "TESTONLY" not in text, path

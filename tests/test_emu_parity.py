@@ -92,3 +92,13 @@ def test_emu_multi_device(emu):
     cfg, streams = scenarios.multi_device(0.5)
     o, res, _ = parity.run_both(cfg, streams, emu, chunk_bytes=300_000)
     parity.compare_streams(cfg, o, res, min_open=500)
+
+
+def test_emu_file_replay_from_a_configuration_file(emu, tmp_path):
+    """Rows f-1/f-2 end to end: configuration text -> ba_conf -> engine; IQ files -> reader threads -> input rings ->
+    ba_cuda_process on the demodulator thread, against the oracle fed the same bytes."""
+    conf, cfg, streams = scenarios.file_replay(tmp_path, 0.45)
+    assert [len(d.channels) for d in cfg.devices] == [4, 3] and cfg.wave_rate == 16000
+    parity.check_channel_info(cfg, emu)
+    o, res = parity.run_files(conf, cfg, streams, emu)
+    parity.compare_streams(cfg, o, res, min_open=500)

@@ -226,3 +226,13 @@ def test_errors(cuda):
         e.submit(0, big)
     assert ei.value.code == -6  # ring overflow reported (circbuffer_append only counts it)
     e.close()
+
+
+def test_file_replay_from_a_configuration_file(cuda, tmp_path):
+    """Rows f-1/f-2 end to end on the GPU: configuration text -> ba_conf -> engine; IQ files (cs16 and cu8) -> reader
+    threads -> pinned input rings -> ba_cuda_process, against the oracle fed the same bytes."""
+    conf, cfg, streams = scenarios.file_replay(tmp_path, 1.6)
+    parity.check_channel_info(cfg, cuda)
+    for chunk in (0, 40_000):
+        o, res = parity.run_files(conf, cfg, streams, cuda, chunk_bytes=chunk)
+        parity.compare_streams(cfg, o, res, min_open=5000)
