@@ -13,7 +13,7 @@ import ctypes as C
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 SFMT = {"u8": 1, "s8": 2, "s16": 3, "f32": 4}
 SFMT_BYTES = {"u8": 1, "s8": 1, "s16": 2, "f32": 4}
@@ -60,6 +60,27 @@ class DeviceDesc(C.Structure):
     ]
 
 
+class MixerInputDesc(C.Structure):
+    _fields_ = [("device", C.c_int32), ("channel", C.c_int32), ("ampfactor", C.c_float), ("balance", C.c_float)]
+
+
+class MixerDesc(C.Structure):
+    _fields_ = [("input_count", C.c_int32), ("inputs", C.POINTER(MixerInputDesc))]
+
+
+class MixerOut(C.Structure):
+    _fields_ = [
+        ("n_batches", C.c_int32),
+        ("wave_batch", C.c_int32),
+        ("stereo", C.c_int32),
+        ("pad0", C.c_int32),
+        ("first_batch", C.c_uint64),
+        ("waveout", C.POINTER(C.c_float)),
+        ("waveout_r", C.POINTER(C.c_float)),
+        ("axcindicate", C.POINTER(C.c_int32)),
+    ]
+
+
 class EngineDesc(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32),
@@ -72,6 +93,8 @@ class EngineDesc(C.Structure):
         ("max_batches_per_step", C.c_int32),
         ("flags", C.c_uint32),
         ("ring_bytes", C.c_uint64),
+        ("mixer_count", C.c_int32),
+        ("mixers", C.POINTER(MixerDesc)),
     ]
 
 
@@ -172,6 +195,28 @@ class DeviceCfg:
 
 
 @dataclass
+class MixerInputCfg:
+    """One channel output of type "mixer" (config.cpp:173-194): which channel, its ampfactor and balance."""
+
+    device: int
+    channel: int
+    ampfactor: float = 1.0
+    balance: float = 0.0
+
+
+@dataclass
+class MixerCfg:
+    """One entry of the ``mixers`` section; inputs in connection order (mixer_connect_input, mixer.cpp:55-93)."""
+
+    name: str = ""
+    inputs: List[MixerInputCfg] = field(default_factory=list)
+
+    @property
+    def stereo(self) -> bool:
+        return any(i.balance != 0.0 for i in self.inputs)
+
+
+@dataclass
 class EngineCfg:
     """The globals ``demodulate()`` reads (boondock_airband.cpp:71-90) plus the device list."""
 
@@ -183,6 +228,7 @@ class EngineCfg:
     max_batches_per_step: int = 0
     flags: int = 0
     ring_bytes: int = 0  # 0 = the reference's MIN_BUF_SIZE
+    mixers: List[MixerCfg] = field(default_factory=list)
 
     @property
     def wave_batch(self) -> int:
@@ -225,6 +271,14 @@ def build_desc(cfg: EngineCfg):
         devs[i] = DeviceDesc(SFMT[d.sample_format], d.bytes_per_sample, d.default_fullscale(), int(d.sample_rate),
                              int(d.centerfreq), int(d.tau), len(d.channels), chans)
     keep.append(devs)
+    mixers = (MixerDesc * max(1, len(cfg.mixers)))()
+    for m, mx in enumerate(cfg.mixers):
+        ins = (MixerInputDesc * max(1, len(mx.inputs)))()
+        for j, i in enumerate(mx.inputs):
+            ins[j] = MixerInputDesc(int(i.device), int(i.channel), float(i.ampfactor), float(i.balance))
+        keep.append(ins)
+        mixers[m] = MixerDesc(len(mx.inputs), ins)
+    keep.append(mixers)
     desc = EngineDesc(ABI_VERSION, cfg.fft_size, cfg.wave_rate, cfg.fm_demod, cfg.cuda_device, len(cfg.devices), devs,
-                      cfg.max_batches_per_step, cfg.flags, cfg.ring_bytes)
+                      cfg.max_batches_per_step, cfg.flags, cfg.ring_bytes, len(cfg.mixers), mixers)
     return desc, keep

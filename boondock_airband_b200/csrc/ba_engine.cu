@@ -93,6 +93,7 @@ struct Dev {
     uint32_t* d_bins = nullptr;
     float2* d_spectrum = nullptr;
     std::vector<uint32_t> base_bins;
+    std::vector<int> feeds; /* flat mixer-input indices fed by channels of this input */
     /* arena offsets (elements) */
     size_t wave_off = 0, iq_off = 0, status_off = 0;
     /* plan of the current step */
@@ -100,7 +101,26 @@ struct Dev {
     uint64_t step_frame0 = 0, step_batch0 = 0;
 };
 
+/* mixer_t / mixinput_t as the engine keeps them (row f-4) */
+struct MixInput {
+    int dev = 0, ch = 0;
+    float mult_l = 0.f, mult_r = 0.f;
+    bool enabled = true; /* input_mask, mixer.cpp:96-112 */
+};
+struct Mixer {
+    int first_in = 0, n_in = 0;
+    bool stereo = false;
+    uint64_t emitted = 0; /* batches handed out so far */
+    size_t out_off = 0;   /* floats into the slot's mixer arena: left plane, then right if stereo */
+};
+
 struct Slot {
+    float* d_mix = nullptr;
+    float* h_mix = nullptr;
+    int32_t* d_mix_sig = nullptr;
+    int32_t* h_mix_sig = nullptr;
+    std::vector<int> mix_emit;        /* per mixer: batches mixed by this ticket */
+    std::vector<uint64_t> mix_first;  /* and the number of the first of them */
     float* d_wave = nullptr;
     float* h_wave = nullptr;
     float2* d_iq = nullptr;
@@ -163,6 +183,16 @@ struct ba_engine {
     size_t desc_bytes = 0;
     int max_phases = 1;
     cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    /* mixers (K3) */
+    std::vector<Mixer> mixers;
+    std::vector<MixInput> mix_in;
+    ba::K3In* d_mix_in = nullptr;
+    ba::K3Mixer* d_mixer = nullptr;
+    float* d_fifo = nullptr;
+    uint8_t* d_fifo_sig = nullptr;
+    int fifo_depth = 0;
+    size_t mix_floats = 0;   /* floats of one slot's mixer arena */
+    size_t mix_desc_off = 0; /* where the K3 part of the per-ticket descriptor blob starts */
 };
 
 namespace {
@@ -186,7 +216,17 @@ void free_engine(ba_engine* e) {
         cudaFree(d->d_spectrum);
         delete d;
     }
+    cudaFree(e->d_mix_in);
+    cudaFree(e->d_mixer);
+    cudaFree(e->d_fifo);
+    cudaFree(e->d_fifo_sig);
     for (Slot& s : e->slot) {
+        cudaFree(s.d_mix);
+        cudaFree(s.d_mix_sig);
+        if (s.h_mix)
+            cudaFreeHost(s.h_mix);
+        if (s.h_mix_sig)
+            cudaFreeHost(s.h_mix_sig);
         cudaFree(s.d_wave);
         cudaFree(s.d_iq);
         cudaFree(s.d_trace);
@@ -407,8 +447,11 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
     if (!desc || !out)
         return fail(BA_ERR_BAD_ARG, "null argument");
     *out = nullptr;
-    if (desc->abi_version != BA_CUDA_ABI_VERSION)
-        return fail(BA_ERR_BAD_ARG, "ABI version %d, library speaks %d", desc->abi_version, BA_CUDA_ABI_VERSION);
+    if (desc->abi_version != 1 && desc->abi_version != BA_CUDA_ABI_VERSION)
+        return fail(BA_ERR_BAD_ARG, "ABI version %d, library speaks 1..%d", desc->abi_version, BA_CUDA_ABI_VERSION);
+    const int n_mixers = desc->abi_version >= 2 ? desc->mixer_count : 0; /* version 1 descriptors end before the mixer fields */
+    if (n_mixers < 0 || (n_mixers > 0 && !desc->mixers))
+        return fail(BA_ERR_BAD_ARG, "mixer_count %d without mixers", n_mixers);
     const int N = desc->fft_size;
     if (N < 256 || N > 8192 || (N & (N - 1)))
         return fail(BA_ERR_BAD_SIZE, "fft_size %d is not a power of two in 256..8192", N);
@@ -604,7 +647,64 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
         }
         const size_t nd = e->dev.size();
         e->desc_bytes = (size_t)e->max_phases * nd * (sizeof(K1Device) + sizeof(K2Dyn));
+        /* mixers: inputs connect in descriptor order (mixer_connect_input, mixer.cpp:55-93) */
+        for (int m = 0; m < n_mixers; m++) {
+            const ba_mixer_desc& md = desc->mixers[m];
+            if (md.input_count < 0 || (md.input_count > 0 && !md.inputs))
+                return fail(BA_ERR_BAD_ARG, "mixer %d: bad input list", m);
+            Mixer mx;
+            mx.first_in = (int)e->mix_in.size();
+            mx.n_in = md.input_count;
+            for (int j = 0; j < md.input_count; j++) {
+                const ba_mixer_input_desc& in = md.inputs[j];
+                if (in.device < 0 || in.device >= (int)nd || in.channel < 0 || in.channel >= e->dev[in.device]->C)
+                    return fail(BA_ERR_BAD_ARG, "mixer %d input %d: no channel %d on device %d", m, j, in.channel, in.device);
+                if (!(in.balance >= -1.0f && in.balance <= 1.0f)) /* config.cpp:183-186 */
+                    return fail(BA_ERR_BAD_ARG, "mixer %d input %d: balance out of allowed range <-1.0;1.0>", m, j);
+                MixInput mi;
+                mi.dev = in.device;
+                mi.ch = in.channel;
+                mi.mult_l = in.ampfactor * fminf(1.0f, 1.0f - in.balance); /* ampfactor * ampl, mixer.cpp:79-80,195 */
+                mi.mult_r = in.ampfactor * fminf(1.0f, 1.0f + in.balance);
+                if (in.balance != 0.0f)
+                    mx.stereo = true; /* MM_STEREO, mixer.cpp:82-83 */
+                e->dev[in.device]->feeds.push_back((int)e->mix_in.size());
+                e->mix_in.push_back(mi);
+            }
+            e->mixers.push_back(mx);
+        }
+        if (n_mixers > 0) {
+            e->fifo_depth = 2 * e->max_batches;
+            for (Mixer& mx : e->mixers) {
+                mx.out_off = e->mix_floats;
+                e->mix_floats += (size_t)(mx.stereo ? 2 : 1) * e->max_batches * e->B;
+            }
+            const size_t ni = std::max<size_t>(1, e->mix_in.size());
+            std::vector<K3In> h_in(ni);
+            std::vector<K3Mixer> h_mx(n_mixers);
+            for (size_t i = 0; i < e->mix_in.size(); i++)
+                h_in[i] = K3In{e->mix_in[i].mult_l, e->mix_in[i].mult_r};
+            for (int m = 0; m < n_mixers; m++)
+                h_mx[m] = K3Mixer{e->mixers[m].first_in, e->mixers[m].n_in, e->mixers[m].stereo ? 1 : 0, 0};
+            if (cudaMalloc((void**)&e->d_mix_in, sizeof(K3In) * ni) != cudaSuccess || cudaMalloc((void**)&e->d_mixer, sizeof(K3Mixer) * n_mixers) != cudaSuccess ||
+                cudaMalloc((void**)&e->d_fifo, sizeof(float) * ni * e->fifo_depth * e->B) != cudaSuccess || cudaMalloc((void**)&e->d_fifo_sig, ni * e->fifo_depth) != cudaSuccess)
+                return fail(BA_ERR_NOMEM, "mixer FIFOs for %zu inputs", ni);
+            CU(cudaMemcpy(e->d_mix_in, h_in.data(), sizeof(K3In) * ni, cudaMemcpyHostToDevice));
+            CU(cudaMemcpy(e->d_mixer, h_mx.data(), sizeof(K3Mixer) * n_mixers, cudaMemcpyHostToDevice));
+            CU(cudaMemset(e->d_fifo, 0, sizeof(float) * ni * e->fifo_depth * e->B));
+            CU(cudaMemset(e->d_fifo_sig, 0, ni * e->fifo_depth));
+            e->mix_desc_off = (e->desc_bytes + 15) & ~(size_t)15;
+            e->desc_bytes = e->mix_desc_off + sizeof(K3InDyn) * ni + sizeof(K3MixDyn) * n_mixers;
+        }
         for (Slot& s : e->slot) {
+            if (n_mixers > 0) {
+                if (cudaMalloc((void**)&s.d_mix, sizeof(float) * e->mix_floats) != cudaSuccess || cudaHostAlloc((void**)&s.h_mix, sizeof(float) * e->mix_floats, cudaHostAllocDefault) != cudaSuccess ||
+                    cudaMalloc((void**)&s.d_mix_sig, sizeof(int32_t) * n_mixers * e->max_batches) != cudaSuccess ||
+                    cudaHostAlloc((void**)&s.h_mix_sig, sizeof(int32_t) * n_mixers * e->max_batches, cudaHostAllocDefault) != cudaSuccess)
+                    return fail(BA_ERR_NOMEM, "mixer output arena");
+                s.mix_emit.assign(n_mixers, 0);
+                s.mix_first.assign(n_mixers, 0);
+            }
             if (cudaMalloc((void**)&s.d_wave, sizeof(float) * wave) != cudaSuccess || cudaHostAlloc((void**)&s.h_wave, sizeof(float) * wave, cudaHostAllocDefault) != cudaSuccess ||
                 cudaMalloc((void**)&s.d_status, sizeof(ba_channel_status) * status) != cudaSuccess ||
                 cudaHostAlloc((void**)&s.h_status, sizeof(ba_channel_status) * status, cudaHostAllocDefault) != cudaSuccess ||
@@ -771,7 +871,16 @@ int ba_cuda_advance_device_stream(ba_engine* e, int dev, size_t bytes) {
 
 /* frames this input may run in the coming step without overflowing its pick ring / output rows */
 static uint64_t frame_room(const ba_engine* e, const Dev& d) {
-    const uint64_t limit = (d.batches_done + (uint64_t)e->max_batches) * e->B + BA_E + e->B - 1;
+    uint64_t batch_limit = d.batches_done + (uint64_t)e->max_batches;
+    /* an input may run ahead of the slowest input of a mixer it feeds by what the mixer FIFO holds */
+    for (int fi : d.feeds) {
+        if (!e->mix_in[fi].enabled)
+            continue;
+        for (const Mixer& mx : e->mixers)
+            if (fi >= mx.first_in && fi < mx.first_in + mx.n_in)
+                batch_limit = std::min<uint64_t>(batch_limit, mx.emitted + (uint64_t)e->fifo_depth);
+    }
+    const uint64_t limit = batch_limit * e->B + BA_E + e->B - 1;
     return limit > d.frames_done ? limit - d.frames_done : 0;
 }
 
@@ -994,6 +1103,57 @@ int ba_cuda_process(ba_engine* e) {
             }
         }
     }
+    /* 2b. mixers: batch k of a mixer is mixed once every unmasked input has delivered its batch k; what an input
+     * delivers beyond that is parked in the mixer FIFO */
+    int mix_max_emit = 0, mix_max_stash = 0;
+    K3InDyn* d_in_dyn = nullptr;
+    K3MixDyn* d_mix_dyn = nullptr;
+    if (!e->mixers.empty()) {
+        const size_t ni = std::max<size_t>(1, e->mix_in.size());
+        K3InDyn* h_in_dyn = reinterpret_cast<K3InDyn*>(s.h_desc + e->mix_desc_off);
+        K3MixDyn* h_mix_dyn = reinterpret_cast<K3MixDyn*>(s.h_desc + e->mix_desc_off + sizeof(K3InDyn) * ni);
+        d_in_dyn = reinterpret_cast<K3InDyn*>(s.d_desc + e->mix_desc_off);
+        d_mix_dyn = reinterpret_cast<K3MixDyn*>(s.d_desc + e->mix_desc_off + sizeof(K3InDyn) * ni);
+        for (size_t m = 0; m < e->mixers.size(); m++) {
+            Mixer& mx = e->mixers[m];
+            uint64_t ready = UINT64_MAX;
+            for (int j = 0; j < mx.n_in; j++) {
+                const MixInput& mi = e->mix_in[mx.first_in + j];
+                if (mi.enabled)
+                    ready = std::min<uint64_t>(ready, e->dev[mi.dev]->step_batch0 + (uint64_t)e->dev[mi.dev]->step_batches);
+            }
+            if (ready == UINT64_MAX || ready < mx.emitted)
+                ready = mx.emitted; /* every input masked: the mixer is disabled (mixer.cpp:109-111) */
+            const int n_emit = (int)std::min<uint64_t>(ready - mx.emitted, (uint64_t)e->max_batches);
+            const uint64_t emit_end = mx.emitted + (uint64_t)n_emit;
+            K3MixDyn& y = h_mix_dyn[m];
+            memset(&y, 0, sizeof(y));
+            y.emit0 = mx.emitted;
+            y.n_emit = n_emit;
+            y.out_l = s.d_mix + mx.out_off;
+            y.out_r = mx.stereo ? s.d_mix + mx.out_off + (size_t)e->max_batches * B : nullptr;
+            y.sig = s.d_mix_sig + m * (size_t)e->max_batches;
+            mix_max_emit = std::max(mix_max_emit, n_emit);
+            for (int j = 0; j < mx.n_in; j++) {
+                const MixInput& mi = e->mix_in[mx.first_in + j];
+                const Dev& d = *e->dev[mi.dev];
+                K3InDyn& x = h_in_dyn[mx.first_in + j];
+                memset(&x, 0, sizeof(x));
+                x.wave = s.d_wave + d.wave_off + (size_t)mi.ch * e->stride;
+                x.status = s.d_status + d.status_off + mi.ch;
+                x.status_stride = (uint32_t)d.C;
+                x.enabled = mi.enabled ? 1 : 0;
+                x.batch0 = d.step_batch0;
+                const uint64_t avail_end = d.step_batch0 + (uint64_t)d.step_batches;
+                x.stash_from = std::max<uint64_t>(d.step_batch0, emit_end);
+                x.stash_count = (mi.enabled && avail_end > x.stash_from) ? (int32_t)(avail_end - x.stash_from) : 0;
+                mix_max_stash = std::max(mix_max_stash, x.stash_count);
+            }
+            s.mix_emit[m] = n_emit;
+            s.mix_first[m] = mx.emitted;
+            mx.emitted = emit_end;
+        }
+    }
     CU(cudaMemcpyAsync(s.d_desc, s.h_desc, e->desc_bytes, cudaMemcpyHostToDevice, e->s_in));
 
     CU(cudaEventRecord(s.ev_in, e->s_in));
@@ -1045,6 +1205,21 @@ int ba_cuda_process(ba_engine* e) {
         CU(cudaEventRecord(s.ev_k[4 * ph + 3], k2s));
     }
     s.phases = phases;
+    if (mix_max_emit > 0 || mix_max_stash > 0) {
+        K3Params p;
+        p.in = e->d_mix_in;
+        p.in_dyn = d_in_dyn;
+        p.mixer = e->d_mixer;
+        p.mix_dyn = d_mix_dyn;
+        p.fifo = e->d_fifo;
+        p.fifo_sig = e->d_fifo_sig;
+        p.fifo_depth = e->fifo_depth;
+        p.wave_batch = B;
+        int rc = k3_launch(p, (int)e->mixers.size(), mix_max_emit, (int)e->mix_in.size(), mix_max_stash, k2s);
+        if (rc != 0)
+            return fail(BA_ERR_CUDA, "mixer launch: %s", cudaGetErrorString((cudaError_t)rc));
+        e->launches += (mix_max_emit > 0 ? 1 : 0) + (mix_max_stash > 0 ? 1 : 0);
+    }
 
     CU(cudaEventRecord(s.ev_kdone, k2s));
     CU(cudaStreamWaitEvent(e->s_out, s.ev_kdone, 0));
@@ -1109,6 +1284,11 @@ int ba_cuda_process(ba_engine* e) {
             s.d2h_bytes += sizeof(ba_channel_status) * total_status;
         }
     }
+    if (mix_max_emit > 0) {
+        CU(cudaMemcpyAsync(s.h_mix, s.d_mix, sizeof(float) * e->mix_floats, cudaMemcpyDeviceToHost, e->s_out));
+        CU(cudaMemcpyAsync(s.h_mix_sig, s.d_mix_sig, sizeof(int32_t) * e->mixers.size() * e->max_batches, cudaMemcpyDeviceToHost, e->s_out));
+        s.d2h_bytes += sizeof(float) * e->mix_floats + sizeof(int32_t) * e->mixers.size() * e->max_batches;
+    }
     CU(cudaEventRecord(s.ev_done, e->s_out));
 
     for (size_t di = 0; di < nd; di++) {
@@ -1155,6 +1335,35 @@ int ba_cuda_collect(ba_engine* e, int ticket, int dev, ba_step_out* out) {
     out->trace = s->h_trace ? s->h_trace + d->wave_off : nullptr;
     out->status = s->h_status + d->status_off;
     out->frames_done = s->frames_done[dev];
+    return BA_OK;
+}
+
+int ba_cuda_collect_mixer(ba_engine* e, int ticket, int mixer, ba_mixer_out* out) {
+    Slot* s = find_slot(e, ticket);
+    if (!s)
+        return BA_ERR_BAD_ARG;
+    if (!out || mixer < 0 || mixer >= (int)e->mixers.size())
+        return fail(BA_ERR_BAD_ARG, "no mixer %d", mixer);
+    CU(cudaEventSynchronize(s->ev_done));
+    const Mixer& mx = e->mixers[mixer];
+    memset(out, 0, sizeof(*out));
+    out->n_batches = s->mix_emit[mixer];
+    out->wave_batch = e->B;
+    out->stereo = mx.stereo ? 1 : 0;
+    out->first_batch = s->mix_first[mixer];
+    out->waveout = s->h_mix + mx.out_off;
+    out->waveout_r = mx.stereo ? s->h_mix + mx.out_off + (size_t)e->max_batches * e->B : nullptr;
+    out->axcindicate = s->h_mix_sig + (size_t)mixer * e->max_batches;
+    return BA_OK;
+}
+
+int ba_cuda_mixer_input_mask(ba_engine* e, int mixer, int input, int enabled) {
+    if (!e || mixer < 0 || mixer >= (int)e->mixers.size() || input < 0 || input >= e->mixers[mixer].n_in)
+        return fail(BA_ERR_BAD_ARG, "no input %d on mixer %d", input, mixer);
+    MixInput& mi = e->mix_in[e->mixers[mixer].first_in + input];
+    if (enabled && !mi.enabled) /* the batches it delivered while masked were never parked; the reference has no re-enable either */
+        return fail(BA_ERR_STATE, "mixer %d input %d was disabled and cannot be re-enabled", mixer, input);
+    mi.enabled = enabled != 0;
     return BA_OK;
 }
 

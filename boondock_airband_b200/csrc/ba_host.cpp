@@ -12,6 +12,9 @@
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -508,7 +511,14 @@ struct DeviceModel {
 
 }  // namespace
 
+struct MixerModel {
+    std::string name;
+    std::vector<ba_mixer_input_desc> inputs;
+};
+
 struct ba_conf {
+    std::vector<MixerModel> mixers;
+    std::vector<ba_mixer_desc> mixer_descs;
     ba_engine_desc desc{};
     std::vector<std::unique_ptr<DeviceModel>> devs;
     std::vector<ba_device_desc> dev_descs;
@@ -545,7 +555,7 @@ std::string scalar_text(const Node& n) {
 
 /* the output types parse_outputs() knows (config.cpp:36-265); only what reaches the hot path is kept:
  * a rawfile output sets needs_raw_iq and has_iq_outputs (config.cpp:162) */
-int scan_outputs(const Node& outs, const Node* mixers, int i, int j, bool* has_iq) {
+int scan_outputs(ba_conf& c, const Node& outs, int i, int j, int dev_index, int chan_index, bool* has_iq) {
     int enabled = 0;
     for (int o = 0; o < outs.length(); o++) {
         const Node& out = outs.at(o);
@@ -558,8 +568,17 @@ int scan_outputs(const Node& outs, const Node* mixers, int i, int j, bool* has_i
             *has_iq = true;
         } else if (!strncmp(type, "mixer", 5)) {
             const char* name = out.at("name").as_cstr();
-            if (!mixers || !mixers->exists(name) || disabled(mixers->at(name)))
+            MixerModel* mx = nullptr; /* getmixerbyname(): enabled mixers only */
+            for (MixerModel& cand : c.mixers)
+                if (cand.name == name)
+                    mx = &cand;
+            if (!mx)
                 raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d] outputs.[%d]: unknown mixer \"%s\"", i, j, o, name);
+            const float ampfactor = out.exists("ampfactor") ? out.at("ampfactor").as_float() : 1.0f;
+            const float balance = out.exists("balance") ? out.at("balance").as_float() : 0.0f;
+            if (balance < -1.0f || balance > 1.0f)
+                raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d] outputs.[%d]: balance out of allowed range <-1.0;1.0>", i, j, o);
+            mx->inputs.push_back(ba_mixer_input_desc{dev_index, chan_index, ampfactor, balance}); /* mixer_connect_input, mixer.cpp:55-93 */
         } else {
             raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d] outputs.[%d]: unknown output type", i, j, o);
         }
@@ -569,7 +588,7 @@ int scan_outputs(const Node& outs, const Node* mixers, int i, int j, bool* has_i
 }
 
 /* parse_channels(), config.cpp:312-729, multichannel mode; R = WAVE_RATE of the build being modelled */
-void translate_channels(ba_conf& c, const Node& chans, const Node* mixers, DeviceModel& dev, int i, int R) {
+void translate_channels(ba_conf& c, const Node& chans, DeviceModel& dev, int i, int R) {
     const bool nfm_build = R == 16000;
     bool slot_needs_raw_iq = false; /* channel_t.needs_raw_iq of slot jj survives a dropped channel (the slot is calloc'ed once) */
     for (int j = 0; j < chans.length(); j++) {
@@ -728,7 +747,7 @@ void translate_channels(ba_conf& c, const Node& chans, const Node* mixers, Devic
             d.tau_us = ch.at("tau").as_int();
         const Node& outs = ch.at("outputs");
         bool has_iq = false;
-        if (outs.length() < 1 || scan_outputs(outs, mixers, i, j, &has_iq) < 1)
+        if (outs.length() < 1 || scan_outputs(c, outs, i, j, (int)c.devs.size(), (int)dev.channels.size(), &has_iq) < 1)
             raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: no outputs defined", i, j);
         d.has_iq_outputs = has_iq ? 1 : 0;
         /* needs_raw_iq without a low-pass (bandwidth present but rejected, or inherited from a dropped entry's slot):
@@ -809,7 +828,40 @@ void translate(ba_conf& c, const Node& root, int wave_rate) {
     const Node& devs = root.at("devices");
     if (devs.length() < 1)
         raise(BA_HOST_ERR_CONFIG, "Configuration error: no devices defined");
-    const Node* mixers = root.find("mixers");
+    /* parse_mixers(), config.cpp:838-889: runs before the devices so that channel outputs can name a mixer */
+    if (const Node* mixers = root.find("mixers")) {
+        for (int i = 0; i < mixers->length(); i++) {
+            const Node& mn = mixers->at(i);
+            if (mn.kind != conf::K_GROUP)
+                mn.bad_type();
+            if (disabled(mn))
+                continue;
+            if (mn.name.empty())
+                raise(BA_HOST_ERR_CONFIG, "Configuration error: mixers.[%d]: undefined mixer name", i);
+            const int highpass = mn.exists("highpass") ? mn.at("highpass").as_int() : 100;
+            const int lowpass = mn.exists("lowpass") ? mn.at("lowpass").as_int() : 2500;
+            if (lowpass > 0 && lowpass < highpass)
+                raise(BA_HOST_ERR_CONFIG, "Configuration error: mixers.[%d]: lowpass (%d) must be greater than or equal to highpass (%d)", i, lowpass, highpass);
+            const Node& outs = mn.at("outputs");
+            int enabled = 0;
+            for (int o = 0; o < outs.length(); o++) {
+                const Node& out = outs.at(o);
+                if (disabled(out))
+                    continue;
+                const char* type = out.at("type").as_cstr();
+                if (!strncmp(type, "rawfile", 7))
+                    raise(BA_HOST_ERR_CONFIG, "Configuration error: mixers.[%d] outputs[%d]: rawfile output is not allowed for mixers", i, o);
+                if (!strncmp(type, "mixer", 5))
+                    raise(BA_HOST_ERR_CONFIG, "Configuration error: mixers.[%d] outputs.[%d]: mixer output is not allowed for mixers", i, o);
+                if (strncmp(type, "icecast", 7) && strncmp(type, "file", 4) && strncmp(type, "udp_stream", 6) && strncmp(type, "pulse", 5))
+                    raise(BA_HOST_ERR_CONFIG, "Configuration error: mixers.[%d] outputs.[%d]: unknown output type", i, o);
+                enabled++;
+            }
+            if (enabled < 1)
+                raise(BA_HOST_ERR_CONFIG, "Configuration error: mixers.[%d]: no outputs defined", i);
+            c.mixers.push_back(MixerModel{mn.name, {}});
+        }
+    }
     for (int i = 0; i < devs.length(); i++) {
         const Node& dn = devs.at(i);
         if (disabled(dn))
@@ -910,7 +962,7 @@ void translate(ba_conf& c, const Node& root, int wave_rate) {
         const Node& chans = dn.at("channels");
         if (chans.length() < 1)
             raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d]: no channels configured", i);
-        translate_channels(c, chans, mixers, *dev, i, R);
+        translate_channels(c, chans, *dev, i, R);
         if (dev->channels.empty())
             raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d]: no channels enabled", i);
         c.devs.push_back(std::move(dev));
@@ -928,6 +980,10 @@ void translate(ba_conf& c, const Node& root, int wave_rate) {
     c.desc.fm_demod = BA_FM_FAST_ATAN2;
     c.desc.device_count = (int32_t)c.dev_descs.size();
     c.desc.devices = c.dev_descs.data();
+    for (MixerModel& mx : c.mixers)
+        c.mixer_descs.push_back(ba_mixer_desc{(int32_t)mx.inputs.size(), mx.inputs.data()});
+    c.desc.mixer_count = (int32_t)c.mixer_descs.size();
+    c.desc.mixers = c.mixer_descs.data();
 }
 
 int parse_into(const char* text, const std::string& origin, const std::string& dir, int wave_rate, ba_conf** out) {
@@ -987,6 +1043,10 @@ const char* ba_conf_device_setting(const ba_conf* c, int device, const char* key
         if (kv.first == key)
             return kv.second.c_str();
     return nullptr;
+}
+
+const char* ba_conf_mixer_name(const ba_conf* c, int mixer) {
+    return c && mixer >= 0 && mixer < (int)c->mixers.size() ? c->mixers[mixer].name.c_str() : nullptr;
 }
 
 int ba_conf_multiple_demod_threads(const ba_conf* c) { return c ? c->multiple_demod_threads : 0; }
@@ -1171,6 +1231,149 @@ int ba_file_input_stop(ba_file_input* f) {
         fclose(f->fp);
     delete f;
     return BA_OK;
+}
+
+}  // extern "C"
+
+/* ------------------------------------------------------------------------------------------------ output hand-off */
+
+struct ba_handoff {
+    std::mutex lock;
+    std::condition_variable can_fill, can_take;
+    unsigned char* arena = nullptr;
+    size_t slot_bytes = 0, pitch = 0;
+    int slots = 0;
+    std::vector<int> free_list;                   /* slot indices nobody holds */
+    std::deque<std::pair<int, uint64_t>> ready;   /* published, oldest first: (slot, tag) */
+    std::vector<uint8_t> state;                   /* 0 free, 1 being filled, 2 published, 3 being read */
+    bool closed = false;
+    std::atomic<uint64_t> overruns{0};
+};
+
+namespace {
+
+int slot_index(const ba_handoff* h, const void* slot) {
+    const unsigned char* p = (const unsigned char*)slot;
+    if (!h || !slot || p < h->arena || p >= h->arena + h->pitch * h->slots || (size_t)(p - h->arena) % h->pitch)
+        return -1;
+    return (int)((size_t)(p - h->arena) / h->pitch);
+}
+
+template <class Pred>
+bool wait_on(std::condition_variable& cv, std::unique_lock<std::mutex>& g, int timeout_ms, Pred pred) {
+    if (timeout_ms < 0) {
+        cv.wait(g, pred);
+        return true;
+    }
+    return cv.wait_for(g, std::chrono::milliseconds(timeout_ms), pred);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ba_handoff_create(int slots, size_t slot_bytes, ba_handoff** out) {
+    if (slots < 1 || slot_bytes == 0 || !out)
+        return fail(BA_ERR_BAD_ARG, "bad argument");
+    *out = nullptr;
+    std::unique_ptr<ba_handoff> h(new (std::nothrow) ba_handoff);
+    if (!h)
+        return fail(BA_ERR_NOMEM, "out of memory");
+    h->pitch = (slot_bytes + 63) & ~(size_t)63;
+    h->slot_bytes = slot_bytes;
+    h->slots = slots;
+    h->arena = (unsigned char*)aligned_alloc(64, h->pitch * (size_t)slots);
+    if (!h->arena)
+        return fail(BA_ERR_NOMEM, "%d hand-off slots of %zu bytes", slots, slot_bytes);
+    h->state.assign(slots, 0);
+    for (int i = slots - 1; i >= 0; i--)
+        h->free_list.push_back(i);
+    *out = h.release();
+    return BA_OK;
+}
+
+int ba_handoff_acquire(ba_handoff* h, int timeout_ms, void** slot) {
+    if (!h || !slot)
+        return fail(BA_ERR_BAD_ARG, "bad argument");
+    std::unique_lock<std::mutex> g(h->lock);
+    const bool ok = wait_on(h->can_fill, g, timeout_ms, [&] { return h->closed || !h->free_list.empty(); });
+    if (h->closed)
+        return BA_HANDOFF_CLOSED;
+    if (!ok) {
+        h->overruns++; /* the consumer has not kept up: output_overrun_count++, boondock_airband.cpp:673-676 */
+        return BA_HANDOFF_TIMEOUT;
+    }
+    const int i = h->free_list.back();
+    h->free_list.pop_back();
+    h->state[i] = 1;
+    *slot = h->arena + h->pitch * (size_t)i;
+    return BA_OK;
+}
+
+int ba_handoff_publish(ba_handoff* h, void* slot, uint64_t tag) {
+    const int i = slot_index(h, slot);
+    if (i < 0)
+        return fail(BA_ERR_BAD_ARG, "not a slot of this hand-off");
+    {
+        std::lock_guard<std::mutex> g(h->lock);
+        if (h->state[i] != 1)
+            return fail(BA_ERR_STATE, "slot %d was not acquired", i);
+        h->state[i] = 2;
+        h->ready.emplace_back(i, tag);
+    }
+    h->can_take.notify_one();
+    return BA_OK;
+}
+
+int ba_handoff_take(ba_handoff* h, int timeout_ms, void** slot, uint64_t* tag) {
+    if (!h || !slot)
+        return fail(BA_ERR_BAD_ARG, "bad argument");
+    std::unique_lock<std::mutex> g(h->lock);
+    const bool ok = wait_on(h->can_take, g, timeout_ms, [&] { return h->closed || !h->ready.empty(); });
+    if (h->ready.empty())
+        return h->closed ? BA_HANDOFF_CLOSED : (ok ? BA_HANDOFF_CLOSED : BA_HANDOFF_TIMEOUT);
+    const std::pair<int, uint64_t> r = h->ready.front();
+    h->ready.pop_front();
+    h->state[r.first] = 3;
+    *slot = h->arena + h->pitch * (size_t)r.first;
+    if (tag)
+        *tag = r.second;
+    return BA_OK;
+}
+
+int ba_handoff_release(ba_handoff* h, void* slot) {
+    const int i = slot_index(h, slot);
+    if (i < 0)
+        return fail(BA_ERR_BAD_ARG, "not a slot of this hand-off");
+    {
+        std::lock_guard<std::mutex> g(h->lock);
+        if (h->state[i] != 3)
+            return fail(BA_ERR_STATE, "slot %d was not taken", i);
+        h->state[i] = 0;
+        h->free_list.push_back(i);
+    }
+    h->can_fill.notify_one();
+    return BA_OK;
+}
+
+void ba_handoff_close(ba_handoff* h) {
+    if (!h)
+        return;
+    {
+        std::lock_guard<std::mutex> g(h->lock);
+        h->closed = true;
+    }
+    h->can_fill.notify_all();
+    h->can_take.notify_all();
+}
+
+uint64_t ba_handoff_overruns(const ba_handoff* h) { return h ? h->overruns.load() : 0; }
+
+void ba_handoff_destroy(ba_handoff* h) {
+    if (!h)
+        return;
+    free(h->arena);
+    delete h;
 }
 
 }  // extern "C"

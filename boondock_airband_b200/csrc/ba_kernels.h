@@ -4,6 +4,7 @@
  *                                     replaces boondock_airband.cpp:426-516 (and hello_fft + samplefft on the Pi)
  *   K2  demod       (demod.cu)       the per-channel sample loop, boondock_airband.cpp:518-679, with Squelch,
  *                                     CTCSS, NotchFilter, LowpassFilter state resident in HBM between launches
+ *   K3  mixer       (mixer.cu)       mixers summed behind the demodulator, mixer.cpp:114-141,166-257
  */
 #ifndef BA_KERNELS_H
 #define BA_KERNELS_H
@@ -156,6 +157,44 @@ struct K2Params {
 /* n_plain: the first n_plain slots of `order` are plain AM channels (demod_plain_kernel), the rest is general (one warp per
  * channel); s2/fork/join (optional) let the two kernels run concurrently */
 int k2_launch(const K2Params& p, int n_plain, cudaStream_t s, cudaStream_t s2, cudaEvent_t fork, cudaEvent_t join);
+
+/* ------------------------------------------------------------------ K3 (mixer.cu) */
+
+/* one mixer input: constants */
+struct K3In {
+    float mult_l, mult_r; /* ampfactor * ampl, ampfactor * ampr (mixer.cpp:79-81,195-199) */
+};
+/* one mixer input, per launch */
+struct K3InDyn {
+    const float* wave;               /* the channel's row of this step's waveout arena */
+    const ba_channel_status* status; /* &status[0][channel] of this step */
+    uint32_t status_stride;          /* channels of the input's device: entries between consecutive batches */
+    int32_t enabled;                 /* input_mask */
+    uint64_t batch0;                 /* number of the first batch the device delivers in this step */
+    uint64_t stash_from;             /* batches [stash_from, stash_from + stash_count) go to the FIFO */
+    int32_t stash_count, pad0;
+};
+struct K3Mixer {
+    int32_t first_in, n_in, stereo, pad0;
+};
+struct K3MixDyn {
+    uint64_t emit0; /* number of the first batch mixed in this step */
+    int32_t n_emit, pad0;
+    float* out_l;
+    float* out_r;
+    int32_t* sig;
+};
+struct K3Params {
+    const K3In* in;
+    const K3InDyn* in_dyn;
+    const K3Mixer* mixer;
+    const K3MixDyn* mix_dyn;
+    float* fifo;       /* [inputs][fifo_depth][B] */
+    uint8_t* fifo_sig; /* [inputs][fifo_depth] */
+    int32_t fifo_depth, wave_batch;
+};
+/* mixes max_emit (largest n_emit of any mixer) batches, then parks max_stash (largest stash_count) */
+int k3_launch(const K3Params& p, int n_mixers, int max_emit, int n_inputs, int max_stash, cudaStream_t s);
 
 }  // namespace ba
 #endif

@@ -27,7 +27,7 @@ _LIBS = {}
 SYMBOLS = (
     "ba_cuda_create", "ba_cuda_destroy", "ba_cuda_last_error", "ba_cuda_visible_devices", "ba_cuda_input_ring",
     "ba_cuda_submit", "ba_cuda_input_space", "ba_cuda_commit", "ba_cuda_submit_external", "ba_cuda_attach_device_stream",
-    "ba_cuda_advance_device_stream", "ba_cuda_process", "ba_cuda_collect", "ba_cuda_ticket_ms", "ba_cuda_step_bytes",
+    "ba_cuda_advance_device_stream", "ba_cuda_process", "ba_cuda_collect", "ba_cuda_collect_mixer", "ba_cuda_mixer_input_mask", "ba_cuda_ticket_ms", "ba_cuda_step_bytes",
     "ba_cuda_channel_info", "ba_cuda_window", "ba_cuda_debug_frames", "ba_cuda_debug_picks",
     "ba_cuda_debug_inject_picks", "ba_cuda_launch_count", "ba_cuda_kernel_ms", "ba_cuda_copy_ms", "ba_cuda_mark", "ba_cuda_mark_ms",
 )
@@ -70,6 +70,8 @@ def load_library(path: Optional[str] = None):
     L.ba_cuda_debug_picks.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, C.c_int, vp]
     L.ba_cuda_debug_inject_picks.argtypes = [vp, C.c_int, vp, C.c_int]
     L.ba_cuda_input_space.argtypes = [vp, C.c_int, C.POINTER(C.c_size_t)]
+    L.ba_cuda_collect_mixer.argtypes = [vp, C.c_int, C.c_int, C.POINTER(abi.MixerOut)]
+    L.ba_cuda_mixer_input_mask.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.ba_cuda_launch_count.argtypes = [vp, u64p]
     L.ba_cuda_kernel_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     L.ba_cuda_copy_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
@@ -186,6 +188,21 @@ class Engine:
     def collect(self, ticket: int, dev: int) -> StepResult:
         return StepResult(self.collect_raw(ticket, dev))
 
+    def collect_mixer(self, ticket: int, mixer: int) -> dict:
+        """What mixer_thread would hand on for this step: dict(first_batch, left [n], right [n] or None, axcindicate [n_batches])."""
+        out = abi.MixerOut()
+        self._check("ba_cuda_collect_mixer", self.L.ba_cuda_collect_mixer(self.h, ticket, mixer, C.byref(out)))
+        n = out.n_batches * out.wave_batch
+        left = np.ctypeslib.as_array(out.waveout, shape=(n,)).copy() if n else np.zeros(0, np.float32)
+        right = None
+        if out.stereo:
+            right = np.ctypeslib.as_array(out.waveout_r, shape=(n,)).copy() if n else np.zeros(0, np.float32)
+        sig = np.ctypeslib.as_array(out.axcindicate, shape=(out.n_batches,)).copy() if out.n_batches else np.zeros(0, np.int32)
+        return dict(first_batch=int(out.first_batch), n_batches=int(out.n_batches), left=left, right=right, axcindicate=sig)
+
+    def mixer_input_mask(self, mixer: int, input: int, enabled: bool):
+        self._check("ba_cuda_mixer_input_mask", self.L.ba_cuda_mixer_input_mask(self.h, mixer, input, 1 if enabled else 0))
+
     def ticket_ms(self, ticket: int) -> float:
         ms = C.c_float()
         self._check("ba_cuda_ticket_ms", self.L.ba_cuda_ticket_ms(self.h, ticket, C.byref(ms)))
@@ -289,6 +306,7 @@ class Engine:
         return self._finish_acc(acc)
 
     def _new_acc(self):
+        self.mixed = [dict(left=[], right=[], axcindicate=[], next_batch=0) for _ in self.cfg.mixers]
         return [dict(waveout=[], iq_out=[], trace=[], status=[], frames_done=0) for _ in self.cfg.devices]
 
     def _step_into(self, acc):
@@ -308,7 +326,26 @@ class Engine:
                     acc[d]["trace"].append(r.trace)
                 for b in range(r.n_batches):
                     acc[d]["status"].append([r.status(b, c) for c in range(r.channel_count)])
+        for m, a in enumerate(self.mixed):
+            r = self.collect_mixer(t, m)
+            if r["n_batches"]:
+                assert r["first_batch"] == a["next_batch"], (m, r["first_batch"], a["next_batch"])
+                a["next_batch"] += r["n_batches"]
+                a["left"].append(r["left"])
+                if r["right"] is not None:
+                    a["right"].append(r["right"])
+                a["axcindicate"].append(r["axcindicate"])
+                produced = True
         return produced, advanced
+
+    def mixer_results(self):
+        """After run_stream / run_file_inputs: per mixer dict(left, right or None, axcindicate)."""
+        out = []
+        for m, a in enumerate(self.mixed):
+            cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dt)
+            out.append(dict(left=cat(a["left"], np.float32), right=cat(a["right"], np.float32) if self.cfg.mixers[m].stereo else None,
+                            axcindicate=cat(a["axcindicate"], np.int32)))
+        return out
 
     def _finish_acc(self, acc):
         out = []

@@ -23,10 +23,13 @@ INPUT_UNKNOWN, INPUT_INITIALIZED, INPUT_RUNNING, INPUT_FAILED, INPUT_STOPPED = r
 # every symbol include/ba_host.h declares
 SYMBOLS = (
     "ba_conf_parse_file", "ba_conf_parse_text", "ba_conf_free", "ba_host_last_error", "ba_conf_engine_desc",
-    "ba_conf_device_count", "ba_conf_device_setting", "ba_conf_multiple_demod_threads", "ba_conf_warnings",
+    "ba_conf_device_count", "ba_conf_device_setting", "ba_conf_mixer_name", "ba_conf_multiple_demod_threads", "ba_conf_warnings",
     "ba_conf_channel_source_index", "ba_file_input_open", "ba_file_input_start", "ba_file_input_state",
     "ba_file_input_bytes", "ba_file_input_stop", "ba_file_input_sink_for_engine", "ba_file_input_sink_release",
+    "ba_handoff_create", "ba_handoff_acquire", "ba_handoff_publish", "ba_handoff_take", "ba_handoff_release", "ba_handoff_close",
+    "ba_handoff_overruns", "ba_handoff_destroy",
 )
+HANDOFF_TIMEOUT, HANDOFF_CLOSED = -30, -31
 
 
 class RingSink(C.Structure):
@@ -69,6 +72,8 @@ def load_library(path: Optional[str] = None):
     L.ba_conf_device_count.argtypes = [vp]
     L.ba_conf_device_setting.argtypes = [vp, C.c_int, C.c_char_p]
     L.ba_conf_device_setting.restype = C.c_char_p
+    L.ba_conf_mixer_name.argtypes = [vp, C.c_int]
+    L.ba_conf_mixer_name.restype = C.c_char_p
     L.ba_conf_multiple_demod_threads.argtypes = [vp]
     L.ba_conf_warnings.argtypes = [vp]
     L.ba_conf_warnings.restype = C.c_char_p
@@ -82,6 +87,17 @@ def load_library(path: Optional[str] = None):
     L.ba_file_input_sink_for_engine.argtypes = [vp, C.c_int, vp, vp, C.POINTER(RingSink)]
     L.ba_file_input_sink_release.argtypes = [C.POINTER(RingSink)]
     L.ba_file_input_sink_release.restype = None
+    L.ba_handoff_create.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp)]
+    L.ba_handoff_acquire.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.ba_handoff_publish.argtypes = [vp, vp, C.c_uint64]
+    L.ba_handoff_take.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.ba_handoff_release.argtypes = [vp, vp]
+    L.ba_handoff_close.argtypes = [vp]
+    L.ba_handoff_close.restype = None
+    L.ba_handoff_overruns.argtypes = [vp]
+    L.ba_handoff_overruns.restype = C.c_uint64
+    L.ba_handoff_destroy.argtypes = [vp]
+    L.ba_handoff_destroy.restype = None
     _LIB[path] = L
     return L
 
@@ -108,6 +124,10 @@ class Config:
                     squelch_threshold=c.squelch_threshold_dbfs, squelch_snr_threshold=c.squelch_snr_threshold, notch=c.notch,
                     notch_q=c.notch_q, ctcss=c.ctcss, bandwidth=c.bandwidth, tau=c.tau_us, has_iq_outputs=bool(c.has_iq_outputs)))
             cfg.devices.append(dev)
+        for m in range(d.mixer_count):
+            md = d.mixers[m]
+            cfg.mixers.append(abi.MixerCfg(L.ba_conf_mixer_name(handle, m).decode(), [
+                abi.MixerInputCfg(md.inputs[j].device, md.inputs[j].channel, md.inputs[j].ampfactor, md.inputs[j].balance) for j in range(md.input_count)]))
         self.cfg = cfg
         self.multiple_demod_threads = bool(L.ba_conf_multiple_demod_threads(handle))
         w = L.ba_conf_warnings(handle).decode()

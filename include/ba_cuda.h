@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BA_CUDA_ABI_VERSION 1
+#define BA_CUDA_ABI_VERSION 2 /* 2 appends mixer_count / mixers to ba_engine_desc; a caller saying 1 is served without them */
 
 #if defined(__GNUC__)
 #define BA_API __attribute__((visibility("default")))
@@ -104,6 +104,20 @@ typedef struct ba_device_desc {
     const ba_channel_desc* channels;
 } ba_device_desc;
 
+/* One mixer input = one channel output of type "mixer" (mixer_connect_input, src/mixer.cpp:55-93; config.cpp:173-194). */
+typedef struct ba_mixer_input_desc {
+    int32_t device;  /* index into ba_engine_desc.devices */
+    int32_t channel; /* index into that device's channels */
+    float ampfactor; /* output "ampfactor", default 1.0 */
+    float balance;   /* output "balance" -1..1, default 0; any non-zero balance makes the mixer stereo */
+} ba_mixer_input_desc;
+
+/* One mixer_t (src/boondock_airband.h mixer_t, src/mixer.cpp).  Inputs are summed in this order. */
+typedef struct ba_mixer_desc {
+    int32_t input_count;
+    const ba_mixer_input_desc* inputs;
+} ba_mixer_desc;
+
 /* The globals demodulate() reads (src/boondock_airband.cpp:71-90), passed explicitly. */
 typedef struct ba_engine_desc {
     int32_t abi_version;          /* BA_CUDA_ABI_VERSION */
@@ -116,6 +130,9 @@ typedef struct ba_engine_desc {
     int32_t max_batches_per_step; /* capacity: WAVE_BATCH batches per device one ba_cuda_process() may produce; 0 = 8 */
     uint32_t flags;               /* BA_FLAG_* */
     uint64_t ring_bytes;          /* base size of each pinned input ring before rounding; 0 = MIN_BUF_SIZE 2560000 (boondock_airband.h:64) */
+    /* abi_version >= 2: mixers summed on the device behind the demodulator */
+    int32_t mixer_count;
+    const ba_mixer_desc* mixers;
 } ba_engine_desc;
 
 /* Per-channel scalars observers read after every batch
@@ -145,6 +162,19 @@ typedef struct ba_step_out {
     const ba_channel_status* status; /* [batch][channel] */
     uint64_t frames_done;  /* FFT frames consumed from this device's stream so far */
 } ba_step_out;
+
+/* What one ba_cuda_process() mixed for one mixer: the batches every unmasked input had delivered by the end of the step
+ * (mixer_thread's output, src/mixer.cpp:166-257, with batch numbers taking the place of its 1/16 s timer). */
+typedef struct ba_mixer_out {
+    int32_t n_batches;      /* whole batches mixed in this step (0..max_batches_per_step) */
+    int32_t wave_batch;
+    int32_t stereo;         /* channel.mode == MM_STEREO */
+    int32_t pad0;
+    uint64_t first_batch;   /* number of the first of them (batches count from 0 per mixer) */
+    const float* waveout;   /* [n_batches*wave_batch] left (or mono) */
+    const float* waveout_r; /* right, NULL for a mono mixer */
+    const int32_t* axcindicate; /* [n_batches] BA_SIGNAL if any input had signal in that batch, else BA_NO_SIGNAL */
+} ba_mixer_out;
 
 /* Derived per-channel constants, for inspection and parity tests. */
 typedef struct ba_channel_info {
@@ -210,6 +240,10 @@ BA_API int ba_cuda_process(ba_engine* e);
  * waveavail=1 + Signal::send(), src/boondock_airband.cpp:673-679,728).  Pointers stay valid until
  * three more ba_cuda_process() calls have been made. */
 BA_API int ba_cuda_collect(ba_engine* e, int ticket, int dev, ba_step_out* out);
+/* Same for mixer `mixer` of the engine descriptor: what mixer_thread would hand to the output thread (src/mixer.cpp:166-257). */
+BA_API int ba_cuda_collect_mixer(ba_engine* e, int ticket, int mixer, ba_mixer_out* out);
+/* mixer_disable_input() (src/mixer.cpp:96-112): a masked input is neither waited for nor summed.  enabled != 0 unmasks. */
+BA_API int ba_cuda_mixer_input_mask(ba_engine* e, int mixer, int input, int enabled);
 /* Device time (ms) between the first and last GPU operation of a finished ticket. */
 BA_API int ba_cuda_ticket_ms(ba_engine* e, int ticket, float* ms);
 

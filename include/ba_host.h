@@ -10,6 +10,9 @@
  *                    a reader thread that appends to the input's ring with the arithmetic of circbuffer_append
  *                    (src/input-helpers.cpp:37-63) and waits for a full ring in 20 us .. 1 ms naps instead of 10 ms per poll.
  *
+ *   ba_handoff_*     the demodulator -> output thread hand-off (waveavail + Signal, boondock_airband.cpp:673-679,728;
+ *                    output.cpp:899-961) with N slots and back-pressure instead of one slot and overruns (row f-4).
+ *
  * Nothing here touches CUDA; libba_host.so loads on a machine without a GPU.  The engine is reached only through the
  * function pointers of ba_ring_sink, which ba_file_input_sink_for_engine() fills from libba_cuda.so's entry points.
  */
@@ -55,6 +58,9 @@ BA_HOST_API int ba_conf_device_count(const ba_conf* c);
 /* Settings of the i-th enabled device the input driver reads itself: "type", "filepath", "speedup_factor", "sample_format",
  * "index", "serial", "gain", "device_string", ...  Strings come back as written, numbers formatted with %.17g. NULL if absent. */
 BA_HOST_API const char* ba_conf_device_setting(const ba_conf* c, int device, const char* key);
+/* name of the m-th enabled entry of the `mixers` section = ba_engine_desc.mixers[m] (parse_mixers, config.cpp:838-889);
+ * its inputs are the channel outputs of type "mixer" naming it, in the order the reference connects them */
+BA_HOST_API const char* ba_conf_mixer_name(const ba_conf* c, int mixer);
 /* root-level switches demodulate()'s callers read (boondock_airband.cpp:852-893) */
 BA_HOST_API int ba_conf_multiple_demod_threads(const ba_conf* c);
 /* Warnings the reference prints to stderr while parsing (obsolete 'squelch', conflicting thresholds, frequency outside the
@@ -107,6 +113,34 @@ typedef int (*ba_space_fn)(ba_engine* e, int dev, size_t* free_bytes);
 BA_HOST_API int ba_file_input_sink_for_engine(ba_engine* e, int dev, ba_submit_fn submit, ba_space_fn space, ba_ring_sink* out);
 /* frees what ba_file_input_sink_for_engine() put behind out->ctx (after ba_file_input_stop) */
 BA_HOST_API void ba_file_input_sink_release(ba_ring_sink* sink);
+
+/* ---------------------------------------------------------------- output hand-off (row f-4) */
+
+/* The reference hands a batch to the output thread through ONE slot per device: demodulate() sets dev->waveavail = 1 and
+ * Signal::send(); if the slot is still full it counts output_overrun_count and overwrites (boondock_airband.cpp:673-679,
+ * 728; consumer output.cpp:899-961).  That is right at 1x real time and loses audio at many times real time.  This is the
+ * same hand-off with N slots: the producer either waits for a free slot (back-pressure, file replay) or, with timeout 0,
+ * counts an overrun like the reference and carries on (live input).  Slots are `slot_bytes` each, 64-byte aligned, and
+ * reach the consumer in publish order. */
+typedef struct ba_handoff ba_handoff;
+
+#define BA_HANDOFF_TIMEOUT (-30) /* nothing became available within timeout_ms */
+#define BA_HANDOFF_CLOSED (-31)  /* ba_handoff_close() was called (do_exit) and, for the consumer, the queue is drained */
+
+BA_HOST_API int ba_handoff_create(int slots, size_t slot_bytes, ba_handoff** out);
+/* producer: a free slot to fill.  timeout_ms < 0 waits, 0 polls (BA_HANDOFF_TIMEOUT counts as one overrun). */
+BA_HOST_API int ba_handoff_acquire(ba_handoff* h, int timeout_ms, void** slot);
+/* producer: hand the filled slot over with a caller-defined tag (device index, batch number ...); wakes a consumer
+ * (the Signal::send() of boondock_airband.cpp:728) */
+BA_HOST_API int ba_handoff_publish(ba_handoff* h, void* slot, uint64_t tag);
+/* consumer: the oldest published slot (the Signal::wait() + waveavail test of output.cpp:908-931) */
+BA_HOST_API int ba_handoff_take(ba_handoff* h, int timeout_ms, void** slot, uint64_t* tag);
+/* consumer: done with it (waveavail = 0, output.cpp:951) */
+BA_HOST_API int ba_handoff_release(ba_handoff* h, void* slot);
+/* do_exit: wakes every waiter; producers get BA_HANDOFF_CLOSED at once, consumers after the queue has drained */
+BA_HOST_API void ba_handoff_close(ba_handoff* h);
+BA_HOST_API uint64_t ba_handoff_overruns(const ba_handoff* h); /* output_overrun_count */
+BA_HOST_API void ba_handoff_destroy(ba_handoff* h);
 
 #ifdef __cplusplus
 }

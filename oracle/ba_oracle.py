@@ -258,3 +258,43 @@ def ctcss_run(hz, rate, window, x, ref=False):
     enough = C.c_int32(0)
     tone = L.ba_oracle_ctcss_run(hz, rate, window, _ptr(x), x.size, C.byref(enough))
     return bool(tone), bool(enough.value)
+
+
+def mix_reference(cfg: abi.EngineCfg, oracles_waveout, oracles_status, mixer: abi.MixerCfg, masked=()):
+    """Restates the summing of the reference's mixer (src/mixer.cpp) for batches paired by number.
+
+    mixer_put_samples (mixer.cpp:114-131): an input's batch is waveout[0..WAVE_BATCH) of its channel plus
+    has_signal = (axcindicate != NO_SIGNAL) (output.cpp:562-564).  mixer_thread (mixer.cpp:183-206): waveout (and
+    waveout_r for MM_STEREO) start at zero, then for every unmasked input with signal, in input order,
+    mix_waveforms adds in[s] * (ampfactor * ampl) — product and sum rounded to float separately — unless the factor
+    is zero (mixer.cpp:133-141); axcindicate = SIGNAL if any input had signal.  ampl = min(1, 1 - balance),
+    ampr = min(1, 1 + balance) (mixer.cpp:79-81).
+
+    oracles_waveout(dev, ch) -> float32 [n], oracles_status(dev, ch) -> list of per-batch status with .axcindicate.
+    Returns (left, right or None, axcindicate per batch) for the batches every unmasked input has delivered.
+    """
+    B = cfg.wave_batch
+    live = [(j, i) for j, i in enumerate(mixer.inputs) if j not in masked]
+    if not live:
+        return np.zeros(0, np.float32), (np.zeros(0, np.float32) if mixer.stereo else None), np.zeros(0, np.int32)
+    waves = {j: oracles_waveout(i.device, i.channel) for j, i in live}
+    stats = {j: oracles_status(i.device, i.channel) for j, i in live}
+    n_batches = min(len(s) for s in stats.values())
+    left = np.zeros(n_batches * B, np.float32)
+    right = np.zeros(n_batches * B, np.float32) if mixer.stereo else None
+    sig = np.full(n_batches, abi.NO_SIGNAL, np.int32)
+    for k in range(n_batches):
+        sl = slice(k * B, (k + 1) * B)
+        for j, i in live:
+            if stats[j][k].axcindicate == abi.NO_SIGNAL:
+                continue
+            sig[k] = abi.SIGNAL
+            amp = np.float32(i.ampfactor)
+            ml = amp * np.minimum(np.float32(1.0), np.float32(1.0) - np.float32(i.balance))
+            mr = amp * np.minimum(np.float32(1.0), np.float32(1.0) + np.float32(i.balance))
+            x = waves[j][sl].astype(np.float32)
+            if ml != 0:
+                left[sl] = left[sl] + x * np.float32(ml)
+            if right is not None and mr != 0:
+                right[sl] = right[sl] + x * np.float32(mr)
+    return left, right, sig

@@ -104,18 +104,19 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
     std::atomic<unsigned> next(0);
     auto cta_runner = [&]() {
         for (;;) {
-            const unsigned b = next.fetch_add(1);
-            if (b >= grid.x)
+            const unsigned lin = next.fetch_add(1);
+            if (lin >= grid.x * grid.y * grid.z)
                 return;
+            const unsigned b = lin % grid.x, by = (lin / grid.x) % grid.y, bz = lin / (grid.x * grid.y);
             Cta cta(block.x, smem_bytes);
             std::vector<std::thread> th;
             th.reserve(block.x);
             for (unsigned t = 0; t < block.x; t++)
-                th.emplace_back([&, t, b]() {
+                th.emplace_back([&, t, b, by, bz]() {
                     Tls& s = tls();
                     s.cta = &cta;
                     s.tid = {t, 0, 0};
-                    s.bid = {b, 0, 0};
+                    s.bid = {b, by, bz};
                     s.bdim = block;
                     s.gdim = grid;
                     body();
@@ -125,7 +126,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
         }
     };
     std::vector<std::thread> runners;
-    const unsigned n = std::min(max_par, grid.x);
+    const unsigned n = std::min(max_par, grid.x * grid.y * grid.z);
     for (unsigned i = 0; i < n; i++)
         runners.emplace_back(cta_runner);
     for (auto& r : runners)

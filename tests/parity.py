@@ -92,6 +92,48 @@ def run_both(cfg: abi.EngineCfg, streams, lib: str, chunk_bytes: int = 1 << 20, 
     return o, res, launches
 
 
+def check_mixers(cfg: abi.EngineCfg, streams, lib: str, chunk_bytes: int, masked=None):
+    """K3 against the restated mixer: bit-exact on the engine's own channel audio (the mixer's arithmetic alone), and within
+    the audio tolerance on the oracle's (the whole path)."""
+    from oracle.ba_oracle import mix_reference
+    masked = masked or {}
+    o = Oracle(cfg)
+    for d, s in enumerate(streams):
+        o.feed(d, s)
+    e = Engine(cfg, lib)
+    try:
+        for m, js in masked.items():
+            for j in js:
+                e.mixer_input_mask(m, j, False)
+        res = e.run_stream(streams, chunk_bytes=chunk_bytes)
+        mixed = e.mixer_results()
+        launches = e.launch_count()
+    finally:
+        e.close()
+
+    class S:  # the engine's per-batch status rows as objects with .axcindicate
+        def __init__(self, v):
+            self.axcindicate = v
+
+    for m, mx in enumerate(cfg.mixers):
+        own = mix_reference(cfg, lambda d, c: res[d]["waveout"][c], lambda d, c: [S(row[c]["axcindicate"]) for row in res[d]["status"]], mx, masked.get(m, ()))
+        ref = mix_reference(cfg, o.waveout, o.status, mx, masked.get(m, ()))
+        got = mixed[m]
+        n = len(got["left"])
+        assert n > 0 and n == len(own[0]) == len(ref[0]), (m, n, len(own[0]), len(ref[0]))
+        assert np.array_equal(got["left"].view(np.uint32), own[0].view(np.uint32)), "mixer %d: left plane not bit-exact" % m
+        assert np.array_equal(got["axcindicate"], own[2]) and np.array_equal(got["axcindicate"], ref[2])
+        gain = sum(abs(i.ampfactor) for i in mx.inputs)
+        assert float(np.abs(got["left"] - ref[0]).max()) <= TOL_AUDIO * max(1.0, gain)
+        if mx.stereo:
+            assert np.array_equal(got["right"].view(np.uint32), own[1].view(np.uint32)), "mixer %d: right plane not bit-exact" % m
+            assert float(np.abs(got["right"] - ref[1]).max()) <= TOL_AUDIO * max(1.0, gain)
+        else:
+            assert got["right"] is None
+        assert (got["axcindicate"] == abi.SIGNAL).any(), "mixer %d never had signal" % m
+    return mixed, res, launches
+
+
 def run_files(conf, cfg: abi.EngineCfg, streams, lib: str, ref: bool = False, chunk_bytes: int = 0):
     """The file replay: one host.FileInput reader thread per device (as the reference's input threads), the demodulator
     loop on this thread.  The oracle gets the same bytes in one piece."""
@@ -109,6 +151,7 @@ def run_files(conf, cfg: abi.EngineCfg, streams, lib: str, ref: bool = False, ch
         for i in inputs:
             i.start()
         res = e.run_file_inputs(inputs)
+        mixed = e.mixer_results()
         for d, i in enumerate(inputs):
             assert i.state == host.INPUT_FAILED  # end of file disables the input, as input-file.cpp:107-111
             assert i.bytes == np.ascontiguousarray(streams[d]).nbytes
@@ -116,6 +159,15 @@ def run_files(conf, cfg: abi.EngineCfg, streams, lib: str, ref: bool = False, ch
         for i in inputs:
             i.stop()
         e.close()
+    from oracle.ba_oracle import mix_reference
+    for m, mx in enumerate(cfg.mixers):  # mixers named by the configuration file: whole-path check against the oracle
+        left, right, sig = mix_reference(cfg, o.waveout, o.status, mx)
+        got = mixed[m]
+        assert len(left) > 0 and len(got["left"]) == len(left) and np.array_equal(got["axcindicate"], sig)
+        gain = max(1.0, sum(abs(i.ampfactor) for i in mx.inputs))
+        assert float(np.abs(got["left"] - left).max()) <= TOL_AUDIO * gain
+        if mx.stereo:
+            assert float(np.abs(got["right"] - right).max()) <= TOL_AUDIO * gain
     return o, res
 
 

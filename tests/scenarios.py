@@ -71,6 +71,21 @@ def multi_device(seconds=0.5):
     return cfg, streams
 
 
+def mixers_on_multi_device(seconds=0.5):
+    """multi_device() plus three mixers (row f-4): a mono one across all inputs, a stereo one with balances (one input
+    panned fully right, so its left factor is zero), a single-input one.  The inputs run at different rates and lengths,
+    so their batches arrive unevenly and the mixer FIFO is exercised."""
+    from boondock_airband_b200.abi import MixerCfg, MixerInputCfg
+    cfg, streams = multi_device(seconds)
+    cfg.mixers = [
+        MixerCfg("mono", [MixerInputCfg(0, 0), MixerInputCfg(1, 1, ampfactor=0.5), MixerInputCfg(2, 2, ampfactor=2.0)]),
+        MixerCfg("stereo", [MixerInputCfg(0, 1, balance=-0.6), MixerInputCfg(1, 0, ampfactor=0.7, balance=0.3), MixerInputCfg(2, 3, balance=1.0),
+                            MixerInputCfg(0, 0, ampfactor=0.0)]),
+        MixerCfg("single", [MixerInputCfg(0, 3, ampfactor=1.25)]),
+    ]
+    return cfg, streams
+
+
 def squelch_steps(levels, fft_size=512):
     """Picked-bin series with constant magnitudes, the stimulus of test_squelch.cpp (0.05 = noise, 0.75 = signal)."""
     z = np.zeros((len(levels), 1, 2), np.float32)
@@ -82,17 +97,18 @@ FILE_REPLAY_CONF = """
 # two file inputs in one configuration file, as an unmodified airband .conf would name them (rows f-1 / f-2)
 fft_size = 512;
 multiple_demod_threads = false;
+mixers: { both: { %(o)s } };
 devices: (
   { type = "file"; filepath = "%(a)s"; sample_rate = 2.4; centerfreq = 145.0; sample_format = "S16"; speedup_factor = 100;
     channels: (
       { freq = 144.7; modulation = "nfm"; bandwidth = 12500; ctcss = 100.0; notch = 100.0; %(o)s },
-      { freq = 144.85; %(o)s },
+      { freq = 144.85; outputs: ( { type = "mixer"; name = "both"; balance = -0.4; } ); },
       { freq = 145.15; disable = true; %(o)s },
       { freq = 145.3; modulation = "nfm"; outputs: ( { type = "rawfile"; directory = "/tmp"; filename_template = "iq"; } ); },
       { freq = 145.45; bandwidth = "8k"; ampfactor = 1.5; squelch_snr_threshold = 6; %(o)s }
     ); },
   { type = "file"; filepath = "%(b)s"; sample_rate = 2560000; centerfreq = 120000000;
-    channels: ( { freq = 119.5; %(o)s }, { freq = 120.225; afc = 6; %(o)s }, { freq = 120800000; squelch_threshold = -42; %(o)s } ); }
+    channels: ( { freq = 119.5; outputs: ( { type = "mixer"; name = "both"; ampfactor = 0.8; balance = 0.4; } ); }, { freq = 120.225; afc = 6; %(o)s }, { freq = 120800000; squelch_threshold = -42; %(o)s } ); }
 );
 """
 

@@ -43,14 +43,16 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_layouts_match_c(tmp_path):
     src = tmp_path / "sizes.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ba_cuda.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ba_cuda.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    "sizeof(ba_channel_desc),sizeof(ba_device_desc),sizeof(ba_engine_desc),sizeof(ba_channel_status),sizeof(ba_step_out),sizeof(ba_channel_info),"
-                   "offsetof(ba_engine_desc,ring_bytes),offsetof(ba_step_out,frames_done),offsetof(ba_device_desc,channels));return 0;}\n")
+                   "offsetof(ba_engine_desc,ring_bytes),offsetof(ba_step_out,frames_done),offsetof(ba_device_desc,channels),"
+                   "sizeof(ba_mixer_input_desc),sizeof(ba_mixer_desc),sizeof(ba_mixer_out),offsetof(ba_engine_desc,mixers),offsetof(ba_mixer_out,axcindicate));return 0;}\n")
     exe = tmp_path / "sizes"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
     got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
     want = [C.sizeof(abi.ChannelDesc), C.sizeof(abi.DeviceDesc), C.sizeof(abi.EngineDesc), C.sizeof(abi.ChannelStatus), C.sizeof(abi.StepOut), C.sizeof(abi.ChannelInfo),
-            abi.EngineDesc.ring_bytes.offset, abi.StepOut.frames_done.offset, abi.DeviceDesc.channels.offset]
+            abi.EngineDesc.ring_bytes.offset, abi.StepOut.frames_done.offset, abi.DeviceDesc.channels.offset,
+            C.sizeof(abi.MixerInputDesc), C.sizeof(abi.MixerDesc), C.sizeof(abi.MixerOut), abi.EngineDesc.mixers.offset, abi.MixerOut.axcindicate.offset]
     assert got == want
 
 

@@ -99,6 +99,23 @@ def test_emu_file_replay_from_a_configuration_file(emu, tmp_path):
     ba_cuda_process on the demodulator thread, against the oracle fed the same bytes."""
     conf, cfg, streams = scenarios.file_replay(tmp_path, 0.45)
     assert [len(d.channels) for d in cfg.devices] == [4, 3] and cfg.wave_rate == 16000
+    assert [(i.device, i.channel) for i in cfg.mixers[0].inputs] == [(0, 1), (1, 0)] and cfg.mixers[0].stereo
     parity.check_channel_info(cfg, emu)
     o, res = parity.run_files(conf, cfg, streams, emu)
     parity.compare_streams(cfg, o, res, min_open=500)
+
+
+@pytest.mark.parametrize("chunk", [300_000, 1_100_000])
+def test_emu_mixers(emu, chunk):
+    """Row f-4: mixers summed on the device (K3), inputs arriving unevenly from three devices."""
+    cfg, streams = scenarios.mixers_on_multi_device(0.5)
+    mixed, res, _ = parity.check_mixers(cfg, streams, emu, chunk)
+    assert mixed[1]["right"] is not None and mixed[0]["right"] is None
+
+
+def test_emu_mixer_masked_input(emu):
+    """mixer_disable_input (mixer.cpp:96-112): a masked input is neither waited for nor summed."""
+    cfg, streams = scenarios.mixers_on_multi_device(0.5)
+    streams[1] = streams[1][: len(streams[1]) // 3]  # device 1 dies early; without the mask mixers 0 and 1 would stop with it
+    mixed, res, _ = parity.check_mixers(cfg, streams, emu, 400_000, masked={0: [1], 1: [1]})
+    assert len(mixed[0]["left"]) > len(res[1]["waveout"][0])

@@ -236,3 +236,18 @@ def test_file_replay_from_a_configuration_file(cuda, tmp_path):
     for chunk in (0, 40_000):
         o, res = parity.run_files(conf, cfg, streams, cuda, chunk_bytes=chunk)
         parity.compare_streams(cfg, o, res, min_open=5000)
+
+
+@pytest.mark.parametrize("chunk", [300_000, 2_000_000])
+def test_mixers(cuda, chunk):
+    """Row f-4: mixers summed on the device (K3) behind the demodulator; inputs from three devices arrive unevenly."""
+    cfg, streams = scenarios.mixers_on_multi_device(1.5)
+    mixed, res, launches = parity.check_mixers(cfg, streams, cuda, chunk)
+    assert mixed[1]["right"] is not None and launches > 0
+
+
+def test_mixer_masked_input(cuda):
+    cfg, streams = scenarios.mixers_on_multi_device(1.2)
+    streams[1] = streams[1][: len(streams[1]) // 3]
+    mixed, res, _ = parity.check_mixers(cfg, streams, cuda, 400_000, masked={0: [1], 1: [1]})
+    assert len(mixed[0]["left"]) > len(res[1]["waveout"][0])

@@ -190,8 +190,48 @@ def test_missing_and_malformed_structure():
         host.parse_text('devices: ({ type = "rtlsdr"; mode = "scan"; channels: ({ freqs = (1.0, 2.0); %s }); });' % OUT)
     assert ei.value.code == host.ERR_UNSUPPORTED
     # a mixer output naming a defined mixer is fine
-    ok = 'mixers: { m1: { %s }; }; devices: ({ type = "rtlsdr"; centerfreq = 1.0; channels: ({ freq = 1.0; outputs: ({ type = "mixer"; name = "m1"; }); }); });' % OUT
+    ok = 'mixers: { m1: { %s } }; devices: ({ type = "rtlsdr"; centerfreq = 1.0; channels: ({ freq = 1.0; outputs: ({ type = "mixer"; name = "m1"; }); }); });' % OUT
     assert len(host.parse_text(ok).cfg.devices[0].channels) == 1
+
+
+MIXERS = """
+mixers: {
+  tower: { outputs: ( { type = "icecast"; server = "x"; port = 8000; mountpoint = "m"; username = "u"; password = "p"; } ); },
+  off:   { disable = true; %(o)s },
+  wide:  { highpass = 200; lowpass = 3000; %(o)s }
+};
+devices: (
+  { type = "rtlsdr"; centerfreq = 120.0; channels: (
+      { freq = 119.5; outputs: ( { type = "mixer"; name = "tower"; }, { type = "mixer"; name = "wide"; balance = -0.5; ampfactor = 2.0; } ); },
+      { freq = 119.7; squelch_snr_threshold = -1; outputs: ( { type = "mixer"; name = "tower"; } ); },
+      { freq = 119.9; outputs: ( { type = "mixer"; name = "tower"; disable = true; }, { type = "mixer"; name = "wide"; balance = 1.0; }, { type = "file"; directory = "/tmp"; filename_template = "x"; } ); } ); },
+  { disable = true; type = "rtlsdr"; centerfreq = 130.0; channels: ( { freq = 130.1; outputs: ( { type = "mixer"; name = "tower"; } ); } ); },
+  { type = "rtlsdr"; centerfreq = 125.0; channels: ( { freq = 125.1; outputs: ( { type = "mixer"; name = "tower"; ampfactor = 0.5; } ); } ); }
+);
+""" % {"o": OUT}
+
+
+def test_mixers_connect_in_the_references_order():
+    """parse_mixers runs first (config.cpp:838-889); every enabled channel output of type "mixer" then connects as the next
+    input of the mixer it names (config.cpp:173-194, mixer.cpp:55-93).  Disabled mixers do not exist for getmixerbyname."""
+    c = host.parse_text(MIXERS)
+    mx = c.cfg.mixers
+    assert [m.name for m in mx] == ["tower", "wide"]
+    # the dropped channel (squelch_snr_threshold = -1) never reaches its outputs; device indices count enabled devices
+    assert [(i.device, i.channel, i.ampfactor, i.balance) for i in mx[0].inputs] == [(0, 0, 1.0, 0.0), (1, 0, 0.5, 0.0)]
+    assert [(i.device, i.channel, i.ampfactor, i.balance) for i in mx[1].inputs] == [(0, 0, 2.0, -0.5), (0, 1, 1.0, 1.0)]
+    assert not mx[0].stereo and mx[1].stereo
+    for bad, msg in [
+        (MIXERS.replace('name = "wide"; balance = 1.0', 'name = "wide"; balance = 1.5'), "balance out of allowed range"),
+        (MIXERS.replace('name = "wide"; balance = 1.0', 'name = "off"'), 'unknown mixer "off"'),
+        (MIXERS.replace('ampfactor = 0.5', 'ampfactor = 1'), "invalid parameter type"),
+        (MIXERS.replace("highpass = 200; lowpass = 3000;", "highpass = 200; lowpass = 100;"), r"mixers.\[2\]: lowpass \(100\) must be greater"),
+        (MIXERS.replace('tower: { outputs: ( { type = "icecast";', 'tower: { outputs: ( { type = "rawfile";'), "rawfile output is not allowed for mixers"),
+        (MIXERS.replace('tower: { outputs: ( { type = "icecast";', 'tower: { outputs: ( { type = "mixer"; name = "wide";'), "mixer output is not allowed for mixers"),
+        (MIXERS.replace('tower: { outputs: ( { type = "icecast";', 'tower: { outputs: ( { disable = true; type = "icecast";'), r"mixers.\[0\]: no outputs defined"),
+    ]:
+        with pytest.raises(host.ConfigError, match=msg):
+            host.parse_text(bad)
 
 
 def test_missing_type_falls_back_to_rtlsdr_with_the_warning():
@@ -290,6 +330,7 @@ def test_the_references_own_configuration_files():
         c = host.parse_file(path)
         n_entries = len(re.findall(r"^\s*freq\s*=", text, re.M))
         assert sum(len(d.channels) for d in c.cfg.devices) == n_entries, name
+        assert sum(len(m.inputs) for m in c.cfg.mixers) == len(re.findall(r'type\s*=\s*"mixer"', text)), name
         for d in c.cfg.devices:
             for ch in d.channels:
                 b = int(math.ceil((ch.freq + d.sample_rate - d.centerfreq) / float(d.sample_rate // c.cfg.fft_size) - 1.0)) % c.cfg.fft_size
@@ -427,6 +468,66 @@ def test_file_input_errors(tmp_path):
     assert rc == 0 and L.ba_file_input_start(h) == 0
     assert wait_for(lambda: L.ba_file_input_state(h) == host.INPUT_FAILED)  # a refused append fails the input
     assert len(ring.data) == 100 and L.ba_file_input_stop(h) == 0
+
+
+def test_handoff_keeps_order_and_applies_back_pressure():
+    """Row f-4: the waveavail/Signal hand-off (boondock_airband.cpp:673-679,728; output.cpp:899-961) with N slots."""
+    import threading
+    L = host.load_library()
+    h = C.c_void_p()
+    assert L.ba_handoff_create(0, 16, C.byref(h)) == -4
+    assert L.ba_handoff_create(3, 4000, C.byref(h)) == 0
+    n_batches, got, slow = 40, [], 0.002
+
+    def output_thread():
+        slot, tag = C.c_void_p(), C.c_uint64()
+        while True:
+            rc = L.ba_handoff_take(h, -1, C.byref(slot), C.byref(tag))
+            if rc == host.HANDOFF_CLOSED:
+                return
+            assert rc == 0 and slot.value % 64 == 0
+            a = np.ctypeslib.as_array(C.cast(slot, C.POINTER(C.c_float)), shape=(1000,))
+            got.append((tag.value, float(a[0]), float(a[-1])))
+            time.sleep(slow)  # a slow encoder
+            assert L.ba_handoff_release(h, slot) == 0
+
+    t = threading.Thread(target=output_thread)
+    t.start()
+    t0 = time.time()
+    for k in range(n_batches):  # the demodulator: far faster than the consumer
+        slot = C.c_void_p()
+        assert L.ba_handoff_acquire(h, -1, C.byref(slot)) == 0
+        a = np.ctypeslib.as_array(C.cast(slot, C.POINTER(C.c_float)), shape=(1000,))
+        a[:] = k
+        assert L.ba_handoff_publish(h, slot, 1000 + k) == 0
+    produced_in = time.time() - t0
+    L.ba_handoff_close(h)  # do_exit: the consumer drains what is queued, then leaves
+    t.join(10)
+    assert not t.is_alive()
+    assert got == [(1000 + k, float(k), float(k)) for k in range(n_batches)]  # nothing lost, nothing reordered
+    assert produced_in >= (n_batches - 4) * slow  # the producer was held back to the consumer's pace
+    assert L.ba_handoff_overruns(h) == 0
+    slot = C.c_void_p()
+    assert L.ba_handoff_acquire(h, -1, C.byref(slot)) == host.HANDOFF_CLOSED
+    L.ba_handoff_destroy(h)
+
+
+def test_handoff_polling_counts_overruns_like_the_reference():
+    L = host.load_library()
+    h = C.c_void_p()
+    assert L.ba_handoff_create(2, 64, C.byref(h)) == 0
+    s = [C.c_void_p() for _ in range(3)]
+    assert L.ba_handoff_acquire(h, 0, C.byref(s[0])) == 0 and L.ba_handoff_acquire(h, 0, C.byref(s[1])) == 0
+    assert L.ba_handoff_acquire(h, 0, C.byref(s[2])) == host.HANDOFF_TIMEOUT and L.ba_handoff_overruns(h) == 1  # output_overrun_count++
+    assert L.ba_handoff_acquire(h, 5, C.byref(s[2])) == host.HANDOFF_TIMEOUT and L.ba_handoff_overruns(h) == 2
+    taken, tag = C.c_void_p(), C.c_uint64()
+    assert L.ba_handoff_take(h, 0, C.byref(taken), C.byref(tag)) == host.HANDOFF_TIMEOUT  # nothing published yet
+    assert L.ba_handoff_release(h, s[0]) == -7 and L.ba_handoff_publish(h, C.c_void_p(s[0].value + 8), 0) == -4
+    assert L.ba_handoff_publish(h, s[1], 7) == 0 and L.ba_handoff_publish(h, s[1], 7) == -7
+    assert L.ba_handoff_take(h, 0, C.byref(taken), C.byref(tag)) == 0 and taken.value == s[1].value and tag.value == 7
+    assert L.ba_handoff_release(h, taken) == 0
+    assert L.ba_handoff_acquire(h, 0, C.byref(s[2])) == 0 and s[2].value == s[1].value
+    L.ba_handoff_destroy(h)
 
 
 def test_host_header_binding_and_exports_agree():

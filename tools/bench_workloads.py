@@ -29,10 +29,67 @@ def workloads():
         "cfg2x64": ("64 inputs of cfg2's shape on one GPU (2048 NFM/CTCSS channels)", lambda: _replicate(configs.cfg2(), 64)),
         "cfg3": ("8 of the 64 synthetic dongles (one GPU's share): 2.4 Msps u8, fft 512, 16 AM channels each", lambda: configs.cfg3(8)),
         "cfg4": ("wideband: 1 input, 61.44 Msps cf32, fft 8192, 2000 mixed AM/NFM channels (250 with CTCSS + notch)", configs.cfg4),
+        "cfg3_mixers": ("cfg3's 8 inputs with 17 mixers summed on the GPU (K3): mixer k = channel k of every input, plus one stereo mixer over input 0", _cfg3_mixers),
         "cfg5_n1024": ("cfg5 at fft 1024: 512 inputs x 2.56 Msps u8, 16 AM channels", lambda: configs.cfg5(512, 1024)),
         "cfg5_n2048": ("cfg5 at fft 2048", lambda: configs.cfg5(512, 2048)),
         "cfg5_n4096": ("cfg5 at fft 4096", lambda: configs.cfg5(512, 4096)),
     }
+
+
+def _cfg3_mixers():
+    from boondock_airband_b200 import configs
+    from boondock_airband_b200.abi import MixerCfg, MixerInputCfg
+    cfg = configs.cfg3(8)
+    for k in range(16):
+        cfg.mixers.append(MixerCfg("m%d" % k, [MixerInputCfg(d, k, ampfactor=0.5) for d in range(8)]))
+    cfg.mixers.append(MixerCfg("stereo", [MixerInputCfg(0, k, balance=(k - 7.5) / 8.0) for k in range(16)]))
+    return cfg
+
+
+def run_file_replay(seconds, ring_bytes):
+    """Row f-1 measured: cfg1's IQ replayed from a file (tmpfs) by the file input's reader thread through the pinned input
+    ring, unpaced, with the demodulator loop on this thread - the path an unmodified input driver takes."""
+    import tempfile
+
+    import numpy as np
+
+    from boondock_airband_b200 import configs, host, synth
+    from boondock_airband_b200.engine import Engine
+
+    cfg = configs.cfg1()
+    cfg.flags = 0
+    cfg.max_batches_per_step = 8
+    cfg.ring_bytes = ring_bytes
+    one = synth.synth(cfg.devices[0], 2.0, 0)
+    reps = int(seconds / 2.0)
+    d = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.NamedTemporaryFile(dir=d, suffix=".cu8") as f:
+        for _ in range(reps):
+            f.write(one.tobytes())
+        f.flush()
+        nbytes = reps * one.nbytes
+        eng = Engine(cfg)
+        inp = host.FileInput(eng, 0, f.name, sample_format="u8", sample_rate=cfg.devices[0].sample_rate, speedup_factor=0.0)
+        t0 = time.perf_counter()
+        inp.start()
+        batches = passes = 0
+        while True:
+            ended = inp.state in (host.INPUT_FAILED, host.INPUT_STOPPED)
+            t = eng.process()
+            r = eng.collect_raw(t, 0)
+            passes += 1
+            batches += r.n_batches
+            if ended and r.n_batches == 0:
+                break
+        wall = time.perf_counter() - t0
+        launches = eng.launch_count()
+        inp.stop()
+        eng.close()
+    samples = nbytes / 2
+    fs = cfg.devices[0].sample_rate
+    return {"workload": "cfg1_file_ring%d" % ring_bytes, "what": "cfg1 replayed from a tmpfs file through the file input's reader thread and the pinned input ring (ring base %d bytes), unpaced" % (ring_bytes or 2560000),
+            "inputs": 1, "channels": 8, "fft_size": 512, "wave_rate": 8000, "signal_seconds": samples / fs, "msps": samples / wall / 1e6, "x_realtime": samples / fs / wall,
+            "process_calls": passes, "batches": batches, "launches_total": launches, "data": "synthetic IQ file; host ring -> H2D -> kernels -> D2H inside the timed region"}
 
 
 def _replicate(cfg, n):
@@ -132,8 +189,12 @@ def main():
     device = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     wl = workloads()
-    names = [n for n in a.only.split(",") if n] or list(wl)
+    names = [n for n in a.only.split(",") if n] or (list(wl) + ["cfg1_file"])
     for n in names:
+        if n.startswith("cfg1_file"):
+            for ring in (0, 64 << 20):
+                print(json.dumps(run_file_replay(40.0, ring)), flush=True)
+            continue
         text, make = wl[n]
         line = run(n, text, make, a.steps, a.warmup, device)
         print(json.dumps(line), flush=True)
