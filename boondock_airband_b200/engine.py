@@ -281,12 +281,14 @@ class Engine:
             fed = False
             for d in range(nd):
                 if pos[d] < views[d].size:
-                    n = min(chunk_bytes, views[d].size - pos[d])
-                    self.submit(d, views[d][pos[d]:pos[d] + n])
-                    pos[d] += n
-                    fed = True
-            produced, _ = self._step_into(acc)
-            if not fed and not produced:
+                    # an input that a mixer holds back (it is ahead of the mixer's other inputs) stops draining its ring
+                    n = min(chunk_bytes, views[d].size - pos[d], self.input_space(d))
+                    if n > 0:
+                        self.submit(d, views[d][pos[d]:pos[d] + n])
+                        pos[d] += n
+                        fed = True
+            produced, advanced = self._step_into(acc)
+            if not fed and not produced and not advanced:
                 break
         return self._finish_acc(acc)
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BA_CUDA_ABI_VERSION 2 /* 2 appends mixer_count / mixers to ba_engine_desc; a caller saying 1 is served without them */
+#define BA_CUDA_ABI_VERSION 2 /* 2: mixers in ba_engine_desc, frequency lists in ba_channel_desc (struct sizes changed: 1 is refused) */
 
 #if defined(__GNUC__)
 #define BA_API __attribute__((visibility("default")))
@@ -70,6 +70,17 @@ enum { BA_SQ_CLOSED = 0, BA_SQ_OPENING = 1, BA_SQ_CLOSING = 2, BA_SQ_LOW_SIGNAL_
 #define BA_TRACE_AUDIO 0x10
 #define BA_TRACE_FILTERED 0x20
 
+/* One freq_t of a scan-mode channel (src/config.cpp:364-433): what the channel may set once per frequency. */
+typedef struct ba_freq_desc {
+    int32_t frequency;              /* "freqs"[f] */
+    int32_t modulation;             /* "modulations"[f] or the channel's "modulation" */
+    float ampfactor;                /* "ampfactor" scalar or list */
+    int32_t squelch_threshold_dbfs; /* "squelch_threshold" scalar or list */
+    float squelch_snr_threshold;    /* "squelch_snr_threshold" scalar or list; <0 = default */
+    float notch, notch_q, ctcss;    /* scalar or list */
+    int32_t bandwidth;              /* scalar or list; <0 = present but rejected */
+} ba_freq_desc;
+
 /*
  * One channel = channel_t + its single freq_t (multichannel mode, src/config.cpp:312-729).
  * Values are the ones written in the libconfig file; every derived constant
@@ -90,6 +101,11 @@ typedef struct ba_channel_desc {
                                     * but its value was rejected: needs_raw_iq is set, no filter (config.cpp:592,609-610) */
     int32_t tau_us;                /* "tau" µs; <0 = inherit the device value (config.cpp:652-656) */
     int32_t has_iq_outputs;        /* channel_t.has_iq_outputs: a rawfile output wants iq_out (config.cpp:162) */
+    /* scan mode (R_SCAN, config.cpp:364-433): freq_count > 0 makes `freqs` the channel's freqlist and the per-frequency
+     * fields above (frequency, modulation, ampfactor, squelch_*, notch*, ctcss, bandwidth) are not read.  The bin and the
+     * derotation step come from freqs[0] (config.cpp:669,684); ba_cuda_set_freq_idx() plays controller_thread's part. */
+    int32_t freq_count;
+    const ba_freq_desc* freqs;
 } ba_channel_desc;
 
 /* One device_t + its input_t (src/boondock_airband.h:272-292, src/input-common.h:39-57). */
@@ -130,7 +146,7 @@ typedef struct ba_engine_desc {
     int32_t max_batches_per_step; /* capacity: WAVE_BATCH batches per device one ba_cuda_process() may produce; 0 = 8 */
     uint32_t flags;               /* BA_FLAG_* */
     uint64_t ring_bytes;          /* base size of each pinned input ring before rounding; 0 = MIN_BUF_SIZE 2560000 (boondock_airband.h:64) */
-    /* abi_version >= 2: mixers summed on the device behind the demodulator */
+    /* mixers summed on the device behind the demodulator */
     int32_t mixer_count;
     const ba_mixer_desc* mixers;
 } ba_engine_desc;
@@ -244,6 +260,12 @@ BA_API int ba_cuda_collect(ba_engine* e, int ticket, int dev, ba_step_out* out);
 BA_API int ba_cuda_collect_mixer(ba_engine* e, int ticket, int mixer, ba_mixer_out* out);
 /* mixer_disable_input() (src/mixer.cpp:96-112): a masked input is neither waited for nor summed.  enabled != 0 unmasks. */
 BA_API int ba_cuda_mixer_input_mask(ba_engine* e, int mixer, int input, int enabled);
+/* Scan mode (row f-3): what controller_thread's `channels[0].freq_idx = i` does (src/boondock_airband.cpp:101-139): from the
+ * next ba_cuda_process() on, the channel runs with freqlist[freq_idx] — its own Squelch, filters, AGC level, modulation,
+ * ampfactor and counters, which resume where they were left (demodulate() reads freq_idx once per batch, :522).
+ * *from_batch (optional) receives the number of the first batch of the device that runs with it.  Retuning the input
+ * (input_set_centerfreq) stays the caller's business. */
+BA_API int ba_cuda_set_freq_idx(ba_engine* e, int dev, int channel, int freq_idx, uint64_t* from_batch);
 /* Device time (ms) between the first and last GPU operation of a finished ticket. */
 BA_API int ba_cuda_ticket_ms(ba_engine* e, int ticket, float* ms);
 

@@ -30,6 +30,7 @@
 #include <complex>
 #include <cstddef>
 #include <thread>
+#include <memory>
 #include <vector>
 
 #include "../include/ba_cuda.h"
@@ -180,18 +181,27 @@ inline float dbfs_to_level(float dbfs, int fft_size) {
     return (float)(pow(10.0, (dbfs - dbfs_offset(fft_size)) / 20.0f) * (size_t)fft_size);
 }
 
-struct Channel {
-    ba_channel_desc cfg;
-    int modulation = 0, afc = 0;
-    int needs_raw_iq = 0, has_iq_outputs = 0;
-    uint32_t dm_dphi = 0, dm_phi = 0;
-    float alpha = 0, pr = 0, pj = 0, prev_waveout = 0.5f;
+/* freq_t (boondock_airband.h:215-230): what scan mode keeps once per frequency of a channel (config.cpp:364-433) */
+struct FreqParms {
+    int modulation = 0;
     float agcavgfast = 0.5f, ampfactor = 1.0f;
     uint32_t active_counter = 0;
-    int axcindicate = BA_NO_SIGNAL;
     Squelch squelch;
     NotchFilter notch;
     LowpassFilter lowpass;
+};
+
+struct Channel {
+    ba_channel_desc cfg;
+    int afc = 0;
+    int needs_raw_iq = 0, has_iq_outputs = 0;
+    uint32_t dm_dphi = 0, dm_phi = 0;
+    float alpha = 0, pr = 0, pj = 0, prev_waveout = 0.5f;
+    int axcindicate = BA_NO_SIGNAL;
+    std::vector<std::unique_ptr<FreqParms>> freqs; /* channel_t.freqlist; one entry in multichannel mode */
+    FreqParms* f = nullptr;                        /* fparms = freqlist + freq_idx, boondock_airband.cpp:522 */
+    int freq_idx = 0;
+    std::vector<std::pair<uint64_t, int>> freq_plan; /* tests: (batch number, freq_idx) the controller thread would have set by then */
     std::vector<float> wavein, waveout, iq_in, iq_out;
     ba_channel_info info;
     /* recorded streams */
@@ -278,6 +288,10 @@ void run_batch(ba_oracle* o, Device& d) {
     const int B = o->wave_batch, E = BA_AGC_EXTRA;
     for (int i = 0; i < (int)d.ch.size(); i++) {
         Channel& c = d.ch[i];
+        for (const auto& pl : c.freq_plan) /* channel->freq_idx as the controller thread left it (.cpp:101-139) */
+            if (pl.first == d.batches)
+                c.freq_idx = pl.second;
+        c.f = c.freqs[c.freq_idx].get(); /* .cpp:522 */
         const int prev_axc = c.axcindicate; /* AFC afc(dev, i) */
         c.axcindicate = BA_NO_SIGNAL;
         float* wavein = c.wavein.data();
@@ -287,9 +301,9 @@ void run_batch(ba_oracle* o, Device& d) {
             float& imag = c.iq_in[2 * (j - E) + 1];
             uint8_t tr = 0;
 
-            c.squelch.process_raw_sample(wavein[j]);
+            c.f->squelch.process_raw_sample(wavein[j]);
 
-            if (c.squelch.should_filter_sample() && c.needs_raw_iq) {
+            if (c.f->squelch.should_filter_sample() && c.needs_raw_iq) {
                 float swf, cwf, re_tmp, im_tmp;
                 g_lut.get(c.dm_phi, &swf, &cwf);
                 /* multiply(real, imag, cwf, -swf, ...) .cpp:141-144,538 */
@@ -297,55 +311,55 @@ void run_batch(ba_oracle* o, Device& d) {
                 im_tmp = imag * cwf + real * (-swf);
                 c.dm_phi += c.dm_dphi;
                 c.dm_phi &= 0xffffff;
-                c.lowpass.apply(re_tmp, im_tmp);
+                c.f->lowpass.apply(re_tmp, im_tmp);
                 real = re_tmp;
                 imag = im_tmp;
                 wavein[j] = sqrtf(real * real + imag * imag); /* sqrt(float) -> float overload, .cpp:548 */
-                if (c.lowpass.enabled())
-                    c.squelch.process_filtered_sample(wavein[j]);
+                if (c.f->lowpass.enabled())
+                    c.f->squelch.process_filtered_sample(wavein[j]);
                 tr |= BA_TRACE_FILTERED;
             }
 
-            if (c.modulation == BA_MOD_AM) {
-                if (c.squelch.first_open_sample()) {
+            if (c.f->modulation == BA_MOD_AM) {
+                if (c.f->squelch.first_open_sample()) {
                     for (int k = j - E; k < j; k++)
-                        if (wavein[k] >= c.squelch.squelch_level())
-                            c.agcavgfast = c.agcavgfast * 0.9f + wavein[k] * 0.1f;
-                } else if (c.squelch.last_open_sample()) {
+                        if (wavein[k] >= c.f->squelch.squelch_level())
+                            c.f->agcavgfast = c.f->agcavgfast * 0.9f + wavein[k] * 0.1f;
+                } else if (c.f->squelch.last_open_sample()) {
                     for (int k = j - E + 1; k < j; k++)
                         wout[k] = wout[k - 1] * 0.94f;
                 }
             }
 
             float& waveout = wout[j];
-            if (c.squelch.should_process_audio()) {
-                if (c.modulation == BA_MOD_AM) {
-                    if (wavein[j] > c.squelch.squelch_level())
-                        c.agcavgfast = c.agcavgfast * 0.995f + wavein[j] * 0.005f;
-                    waveout = (wavein[j - E] - c.agcavgfast) / (c.agcavgfast * 1.5f);
+            if (c.f->squelch.should_process_audio()) {
+                if (c.f->modulation == BA_MOD_AM) {
+                    if (wavein[j] > c.f->squelch.squelch_level())
+                        c.f->agcavgfast = c.f->agcavgfast * 0.995f + wavein[j] * 0.005f;
+                    waveout = (wavein[j - E] - c.f->agcavgfast) / (c.f->agcavgfast * 1.5f);
                     if (fabsf(waveout) > 0.8f) {
                         waveout *= 0.85f;
-                        c.agcavgfast *= 1.15f;
+                        c.f->agcavgfast *= 1.15f;
                     }
-                } else if (c.modulation == BA_MOD_NFM) {
+                } else if (c.f->modulation == BA_MOD_NFM) {
                     if (o->fm_demod == BA_FM_FAST_ATAN2)
                         waveout = disc_polar(real, imag, c.pr, c.pj);
                     else
                         waveout = disc_quadri(real, imag, c.pr, c.pj);
                     c.pr = real;
                     c.pj = imag;
-                    c.agcavgfast = c.agcavgfast * 0.995f + waveout * 0.005f;
-                    waveout -= c.agcavgfast;
+                    c.f->agcavgfast = c.f->agcavgfast * 0.995f + waveout * 0.005f;
+                    waveout -= c.f->agcavgfast;
                     waveout = waveout * (1.0f - c.alpha) + c.prev_waveout * c.alpha;
                     c.prev_waveout = waveout;
                 }
-                c.squelch.process_audio_sample(waveout);
+                c.f->squelch.process_audio_sample(waveout);
                 tr |= BA_TRACE_AUDIO;
             }
 
-            if (c.squelch.is_open()) {
-                c.notch.apply(waveout);
-                waveout *= c.ampfactor;
+            if (c.f->squelch.is_open()) {
+                c.f->notch.apply(waveout);
+                waveout *= c.f->ampfactor;
                 if (isnan(waveout))
                     waveout = 0.0;
                 else if (waveout > 1.0)
@@ -366,7 +380,7 @@ void run_batch(ba_oracle* o, Device& d) {
                 }
             }
             if (o->keep && (o->flags & BA_FLAG_TRACE))
-                c.rec_trace.push_back((uint8_t)(tr | (SQ_CURRENT(c.squelch) & BA_TRACE_STATE_MASK)));
+                c.rec_trace.push_back((uint8_t)(tr | (SQ_CURRENT(c.f->squelch) & BA_TRACE_STATE_MASK)));
         }
         memmove(wavein, wavein + B, (d.waveend - B) * sizeof(float));
         if (c.needs_raw_iq)
@@ -375,7 +389,7 @@ void run_batch(ba_oracle* o, Device& d) {
         afc_finalize(d, i, prev_axc, d.fftout.data(), (size_t)o->fft_size);
 
         if (c.axcindicate != BA_NO_SIGNAL)
-            c.active_counter++;
+            c.f->active_counter++;
 
         /* what output_thread does with the batch (output.cpp:931-951): consume waveout[0..B), keep the tail */
         if (o->keep) {
@@ -385,14 +399,14 @@ void run_batch(ba_oracle* o, Device& d) {
             ba_channel_status st;
             st.axcindicate = c.axcindicate;
             st.bin = (uint32_t)d.bins[i];
-            st.signal_level = c.squelch.signal_level();
-            st.noise_level = c.squelch.noise_level();
-            st.squelch_level = c.squelch.squelch_level();
-            st.open_count = (uint32_t)c.squelch.open_count();
-            st.flappy_count = (uint32_t)c.squelch.flappy_count();
-            st.ctcss_count = (uint32_t)c.squelch.ctcss_count();
-            st.no_ctcss_count = (uint32_t)c.squelch.no_ctcss_count();
-            st.active_counter = c.active_counter;
+            st.signal_level = c.f->squelch.signal_level();
+            st.noise_level = c.f->squelch.noise_level();
+            st.squelch_level = c.f->squelch.squelch_level();
+            st.open_count = (uint32_t)c.f->squelch.open_count();
+            st.flappy_count = (uint32_t)c.f->squelch.flappy_count();
+            st.ctcss_count = (uint32_t)c.f->squelch.ctcss_count();
+            st.no_ctcss_count = (uint32_t)c.f->squelch.no_ctcss_count();
+            st.active_counter = c.f->active_counter;
             c.rec_status.push_back(st);
         } else {
             double s = 0;
@@ -468,11 +482,20 @@ int fill_channel(ba_oracle* o, Device& d, Channel& c, const ba_channel_desc& cd)
     const int R = o->wave_rate, N = o->fft_size;
     const int B = o->wave_batch, E = BA_AGC_EXTRA;
     c.cfg = cd;
-    c.modulation = cd.modulation;
     c.afc = cd.afc & 0xff;
-    c.ampfactor = cd.ampfactor;
     c.has_iq_outputs = cd.has_iq_outputs ? 1 : 0;
-    c.needs_raw_iq = (cd.modulation == BA_MOD_NFM || cd.bandwidth != 0 || cd.has_iq_outputs) ? 1 : 0; /* config.cpp:162,596,674-680 */
+    /* the frequency list: scan mode names it (config.cpp:364-433); otherwise the channel's own fields are freqlist[0] */
+    std::vector<ba_freq_desc> fl;
+    if (cd.freq_count >= 1 && cd.freqs)
+        fl.assign(cd.freqs, cd.freqs + cd.freq_count);
+    else
+        fl.push_back(ba_freq_desc{cd.frequency, cd.modulation, cd.ampfactor, cd.squelch_threshold_dbfs, cd.squelch_snr_threshold, cd.notch, cd.notch_q, cd.ctcss, cd.bandwidth});
+    const int frequency0 = fl[0].frequency; /* bin and dm_dphi come from freqlist[0] only (config.cpp:669,684) */
+    c.needs_raw_iq = cd.has_iq_outputs ? 1 : 0;
+    for (const ba_freq_desc& fd : fl) /* config.cpp:162,596,674-680 */
+        if (fd.modulation == BA_MOD_NFM || fd.bandwidth != 0)
+            c.needs_raw_iq = 1;
+    c.cfg.freqs = nullptr;
     c.wavein.assign(2 * B + E, 0.0f);
     c.waveout.assign(2 * B + E, 0.0f);
     c.iq_in.assign(2 * (2 * B + E), 0.0f);
@@ -489,32 +512,39 @@ int fill_channel(ba_oracle* o, Device& d, Channel& c, const ba_channel_desc& cd)
         alpha = cd.tau_us == 0 ? 0.0f : (float)exp(-1.0f / (R * 1e-6 * cd.tau_us));
     c.alpha = alpha;
 
-    /* squelch settings in the order parse_channels applies them (config.cpp:437-515) */
-    if (cd.squelch_threshold_dbfs < 0)
-        c.squelch.set_squelch_level_threshold(dbfs_to_level((float)cd.squelch_threshold_dbfs, N));
-    if (cd.squelch_snr_threshold >= 0)
-        c.squelch.set_squelch_snr_threshold(cd.squelch_snr_threshold);
-    if (cd.notch > 0) {
-        float q = cd.notch_q == 0.0f ? 10.0f : cd.notch_q;
-        c.notch = NotchFilter(cd.notch, (float)R, q);
+    /* squelch settings in the order parse_channels applies them (config.cpp:437-515), per frequency */
+    for (const ba_freq_desc& fd : fl) {
+        std::unique_ptr<FreqParms> fp(new FreqParms());
+        fp->modulation = fd.modulation;
+        fp->ampfactor = fd.ampfactor;
+        if (fd.squelch_threshold_dbfs < 0)
+            fp->squelch.set_squelch_level_threshold(dbfs_to_level((float)fd.squelch_threshold_dbfs, N));
+        if (fd.squelch_snr_threshold >= 0)
+            fp->squelch.set_squelch_snr_threshold(fd.squelch_snr_threshold);
+        if (fd.notch > 0) {
+            float q = fd.notch_q == 0.0f ? 10.0f : fd.notch_q;
+            fp->notch = NotchFilter(fd.notch, (float)R, q);
+        }
+        if (fd.ctcss > 0)
+            fp->squelch.set_ctcss_freq(fd.ctcss, (float)R);
+        if (fd.bandwidth > 0)
+            fp->lowpass = LowpassFilter((float)fd.bandwidth / 2, (float)R);
+        c.freqs.push_back(std::move(fp));
     }
-    if (cd.ctcss > 0)
-        c.squelch.set_ctcss_freq(cd.ctcss, (float)R);
-    if (cd.bandwidth > 0)
-        c.lowpass = LowpassFilter((float)cd.bandwidth / 2, (float)R);
+    c.f = c.freqs[0].get();
 
     /* bin, config.cpp:669-670: Fs / N is an integer division */
     const int fs = d.cfg.sample_rate, cf = d.cfg.centerfreq;
-    size_t bin = (size_t)ceil((cd.frequency + fs - cf) / (double)((size_t)fs / (size_t)N) - 1.0) % (size_t)N;
+    size_t bin = (size_t)ceil((frequency0 + fs - cf) / (double)((size_t)fs / (size_t)N) - 1.0) % (size_t)N;
     d.bins.push_back(bin);
     d.base_bins.push_back(bin);
 
     if (c.needs_raw_iq) { /* config.cpp:682-715 */
-        double dm = (double)(cd.frequency - cf);
+        double dm = (double)(frequency0 - cf);
         double decim = ((double)fs / (double)R);
         double corr = (double)R / 2.0;
         corr *= (decim - round(decim));
-        corr *= (double)(cd.frequency - cf) / ((double)fs / 2.0);
+        corr *= (double)(frequency0 - cf) / ((double)fs / 2.0);
         dm -= corr;
         dm /= (double)R;
         dm -= trunc(dm);
@@ -530,40 +560,40 @@ int fill_channel(ba_oracle* o, Device& d, Channel& c, const ba_channel_desc& cd)
     in.needs_raw_iq = c.needs_raw_iq;
     in.alpha = c.alpha;
 #ifdef BA_ORACLE_REF
-    in.squelch_ratio = c.squelch.normal_signal_ratio_;
-    in.manual_level = c.squelch.using_manual_level_ ? c.squelch.manual_signal_level_ : 0.0f;
-    in.notch_enabled = c.notch.enabled_;
+    in.squelch_ratio = c.f->squelch.normal_signal_ratio_;
+    in.manual_level = c.f->squelch.using_manual_level_ ? c.f->squelch.manual_signal_level_ : 0.0f;
+    in.notch_enabled = c.f->notch.enabled_;
     if (in.notch_enabled)
-        memcpy(in.notch_d, c.notch.d, sizeof(in.notch_d));
-    in.lowpass_enabled = c.lowpass.enabled_;
+        memcpy(in.notch_d, c.f->notch.d, sizeof(in.notch_d));
+    in.lowpass_enabled = c.f->lowpass.enabled_;
     if (in.lowpass_enabled) {
-        in.lowpass_ycoeffs[0] = c.lowpass.ycoeffs[0];
-        in.lowpass_ycoeffs[1] = c.lowpass.ycoeffs[1];
-        in.lowpass_gain = c.lowpass.gain;
+        in.lowpass_ycoeffs[0] = c.f->lowpass.ycoeffs[0];
+        in.lowpass_ycoeffs[1] = c.f->lowpass.ycoeffs[1];
+        in.lowpass_gain = c.f->lowpass.gain;
     }
-    if (cd.ctcss > 0) {
-        in.ctcss_fast_tones = (int32_t)c.squelch.ctcss_fast_.powers_.tones_.size();
-        in.ctcss_slow_tones = (int32_t)c.squelch.ctcss_slow_.powers_.tones_.size();
-        in.ctcss_fast_window = c.squelch.ctcss_fast_.window_size_;
-        in.ctcss_slow_window = c.squelch.ctcss_slow_.window_size_;
+    if (fl[0].ctcss > 0) {
+        in.ctcss_fast_tones = (int32_t)c.f->squelch.ctcss_fast_.powers_.tones_.size();
+        in.ctcss_slow_tones = (int32_t)c.f->squelch.ctcss_slow_.powers_.tones_.size();
+        in.ctcss_fast_window = c.f->squelch.ctcss_fast_.window_size_;
+        in.ctcss_slow_window = c.f->squelch.ctcss_slow_.window_size_;
     }
 #else
-    in.squelch_ratio = c.squelch.ratio();
-    in.manual_level = c.squelch.manual();
-    in.notch_enabled = c.notch.enabled();
+    in.squelch_ratio = c.f->squelch.ratio();
+    in.manual_level = c.f->squelch.manual();
+    in.notch_enabled = c.f->notch.enabled();
     if (in.notch_enabled)
-        memcpy(in.notch_d, c.notch.coeffs(), sizeof(in.notch_d));
-    in.lowpass_enabled = c.lowpass.enabled();
+        memcpy(in.notch_d, c.f->notch.coeffs(), sizeof(in.notch_d));
+    in.lowpass_enabled = c.f->lowpass.enabled();
     if (in.lowpass_enabled) {
-        in.lowpass_ycoeffs[0] = c.lowpass.ycoeffs()[0];
-        in.lowpass_ycoeffs[1] = c.lowpass.ycoeffs()[1];
-        in.lowpass_gain = c.lowpass.gain();
+        in.lowpass_ycoeffs[0] = c.f->lowpass.ycoeffs()[0];
+        in.lowpass_ycoeffs[1] = c.f->lowpass.ycoeffs()[1];
+        in.lowpass_gain = c.f->lowpass.gain();
     }
-    if (cd.ctcss > 0) {
-        in.ctcss_fast_tones = c.squelch.fast_tones();
-        in.ctcss_slow_tones = c.squelch.slow_tones();
-        in.ctcss_fast_window = c.squelch.fast_window();
-        in.ctcss_slow_window = c.squelch.slow_window();
+    if (fl[0].ctcss > 0) {
+        in.ctcss_fast_tones = c.f->squelch.fast_tones();
+        in.ctcss_slow_tones = c.f->squelch.slow_tones();
+        in.ctcss_fast_window = c.f->squelch.fast_window();
+        in.ctcss_slow_window = c.f->squelch.slow_window();
     }
 #endif
     return 0;
@@ -690,6 +720,17 @@ size_t ba_oracle_status(ba_oracle* o, int dev, int ch, ba_channel_status* out, s
 }
 int ba_oracle_channel_info(ba_oracle* o, int dev, int ch, ba_channel_info* out) {
     *out = o->dev[dev].ch[ch].info;
+    return BA_OK;
+}
+/* scan mode: from batch `from_batch` of the device on, the channel runs with freqlist[freq_idx] — what controller_thread's
+ * `dev->channels[0].freq_idx = i` (boondock_airband.cpp:115-118) amounts to when demodulate() next reads it (:522) */
+int ba_oracle_set_freq_idx(ba_oracle* o, int dev, int ch, uint64_t from_batch, int freq_idx) {
+    if (!o || dev < 0 || dev >= (int)o->dev.size() || ch < 0 || ch >= (int)o->dev[dev].ch.size())
+        return BA_ERR_BAD_ARG;
+    Channel& c = o->dev[dev].ch[ch];
+    if (freq_idx < 0 || freq_idx >= (int)c.freqs.size())
+        return BA_ERR_BAD_ARG;
+    c.freq_plan.emplace_back(from_batch, freq_idx);
     return BA_OK;
 }
 int ba_oracle_window(ba_oracle* o, float* out, size_t count) {

@@ -28,6 +28,7 @@ size_t ba_oracle_picks(ba_oracle* o, int dev, int ch, float* out, size_t count);
 size_t ba_oracle_trace(ba_oracle* o, int dev, int ch, uint8_t* out, size_t count);
 size_t ba_oracle_status(ba_oracle* o, int dev, int ch, ba_channel_status* out, size_t count);
 int ba_oracle_channel_info(ba_oracle* o, int dev, int ch, ba_channel_info* out);
+int ba_oracle_set_freq_idx(ba_oracle* o, int dev, int ch, uint64_t from_batch, int freq_idx);
 int ba_oracle_window(ba_oracle* o, float* out, size_t count);
 int ba_oracle_debug_frames(ba_oracle* o, int dev, const void* iq, size_t bytes, int n_frames, float* fftin, float* fftout);
 double ba_oracle_run_threads(ba_oracle* o, const void* const* iq, const size_t* bytes, int threads);
