@@ -30,6 +30,20 @@ OK = 0
 ERRORS = {-1: "NO_DEVICE", -2: "BAD_SIZE", -3: "NOMEM", -4: "BAD_ARG", -5: "CUDA", -6: "OVERRUN", -7: "STATE"}
 
 
+class FreqDesc(C.Structure):
+    _fields_ = [
+        ("frequency", C.c_int32),
+        ("modulation", C.c_int32),
+        ("ampfactor", C.c_float),
+        ("squelch_threshold_dbfs", C.c_int32),
+        ("squelch_snr_threshold", C.c_float),
+        ("notch", C.c_float),
+        ("notch_q", C.c_float),
+        ("ctcss", C.c_float),
+        ("bandwidth", C.c_int32),
+    ]
+
+
 class ChannelDesc(C.Structure):
     _fields_ = [
         ("frequency", C.c_int32),
@@ -44,6 +58,8 @@ class ChannelDesc(C.Structure):
         ("bandwidth", C.c_int32),
         ("tau_us", C.c_int32),
         ("has_iq_outputs", C.c_int32),
+        ("freq_count", C.c_int32),
+        ("freqs", C.POINTER(FreqDesc)),
     ]
 
 
@@ -155,6 +171,21 @@ class ChannelInfo(C.Structure):
 
 
 @dataclass
+class FreqCfg:
+    """One frequency of a scan-mode channel: the freq_t fields (config.cpp:364-433)."""
+
+    freq: int
+    modulation: str = "am"
+    ampfactor: float = 1.0
+    squelch_threshold: int = 0
+    squelch_snr_threshold: float = -1.0
+    notch: float = 0.0
+    notch_q: float = 0.0
+    ctcss: float = 0.0
+    bandwidth: int = 0
+
+
+@dataclass
 class ChannelCfg:
     """One ``channels[]`` entry of a multichannel device (config.cpp:312-729)."""
 
@@ -170,6 +201,7 @@ class ChannelCfg:
     bandwidth: int = 0
     tau: int = -1  # microseconds, <0 = inherit
     has_iq_outputs: bool = False
+    freqs: List[FreqCfg] = field(default_factory=list)  # scan mode: the channel's frequency list; empty = multichannel
 
 
 @dataclass
@@ -263,10 +295,15 @@ def build_desc(cfg: EngineCfg):
     for i, d in enumerate(cfg.devices):
         chans = (ChannelDesc * len(d.channels))()
         for j, c in enumerate(d.channels):
+            fl = (FreqDesc * max(1, len(c.freqs)))()
+            for k, f in enumerate(c.freqs):
+                fl[k] = FreqDesc(int(f.freq), MOD[f.modulation], float(f.ampfactor), int(f.squelch_threshold), float(f.squelch_snr_threshold),
+                                 float(f.notch), float(f.notch_q), float(f.ctcss), int(f.bandwidth))
+            keep.append(fl)
             chans[j] = ChannelDesc(
                 int(c.freq), MOD[c.modulation], int(c.afc), float(c.ampfactor), int(c.squelch_threshold),
                 float(c.squelch_snr_threshold), float(c.notch), float(c.notch_q), float(c.ctcss), int(c.bandwidth),
-                int(c.tau), 1 if c.has_iq_outputs else 0)
+                int(c.tau), 1 if c.has_iq_outputs else 0, len(c.freqs), fl if c.freqs else None)
         keep.append(chans)
         devs[i] = DeviceDesc(SFMT[d.sample_format], d.bytes_per_sample, d.default_fullscale(), int(d.sample_rate),
                              int(d.centerfreq), int(d.tau), len(d.channels), chans)

@@ -65,6 +65,9 @@ struct ExtChunk {
 struct Dev {
     ba_device_desc cfg;
     std::vector<ba_channel_desc> chans;
+    std::vector<std::vector<ba_freq_desc>> freqs; /* per channel: its freqlist (one entry in multichannel mode) */
+    std::vector<int> freq_idx;                    /* channel_t.freq_idx */
+    std::vector<size_t> bank0;                    /* per channel: first entry of its freq bank (scan channels), else SIZE_MAX */
     int C = 0, c_pad = 0;
     size_t sample_bytes = 0; /* one complex sample */
     size_t hop_bytes = 0, frame_bytes = 0;
@@ -186,6 +189,9 @@ struct ba_engine {
     /* mixers (K3) */
     std::vector<Mixer> mixers;
     std::vector<MixInput> mix_in;
+    /* scan mode: per frequency of every scan channel, the constants and the parked freq_t state */
+    ba::K2Chan* d_bank_chan = nullptr;
+    ba::K2State* d_bank_state = nullptr;
     ba::K3In* d_mix_in = nullptr;
     ba::K3Mixer* d_mixer = nullptr;
     float* d_fifo = nullptr;
@@ -216,6 +222,8 @@ void free_engine(ba_engine* e) {
         cudaFree(d->d_spectrum);
         delete d;
     }
+    cudaFree(e->d_bank_chan);
+    cudaFree(e->d_bank_state);
     cudaFree(e->d_mix_in);
     cudaFree(e->d_mixer);
     cudaFree(e->d_fifo);
@@ -291,9 +299,26 @@ uint64_t frames_admitted(const Dev& d, uint64_t total) {
 }
 
 /* fills K2Chan constants + initial K2State of one channel; mirrors parse_channels (config.cpp:312-729) */
-int setup_channel(ba_engine* e, Dev& d, int ci, ba::K2Chan& k, ba::K2State& st, ba::K2Ctcss* ctcss_pool, int& n_ctcss, ba_channel_info& in) {
+/* the channel descriptor one entry of the frequency list amounts to */
+ba_channel_desc with_freq(const ba_channel_desc& c, const ba_freq_desc& f) {
+    ba_channel_desc r = c;
+    r.frequency = f.frequency;
+    r.modulation = f.modulation;
+    r.ampfactor = f.ampfactor;
+    r.squelch_threshold_dbfs = f.squelch_threshold_dbfs;
+    r.squelch_snr_threshold = f.squelch_snr_threshold;
+    r.notch = f.notch;
+    r.notch_q = f.notch_q;
+    r.ctcss = f.ctcss;
+    r.bandwidth = f.bandwidth;
+    return r;
+}
+
+/* cd: the channel with the fields of ONE frequency; frequency0 / needs_raw_iq: what the channel as a whole derives from
+ * freqlist[0] (bin, dm_dphi: config.cpp:669,684) and from all its frequencies (needs_raw_iq: config.cpp:162,596,674-680) */
+int setup_channel(ba_engine* e, Dev& d, int ci, const ba_channel_desc& cd, int frequency0, int needs_raw_iq, ba::K2Chan& k, ba::K2State& st, ba::K2Ctcss* ctcss_pool,
+                  int& n_ctcss, ba_channel_info& in) {
     using namespace ba;
-    const ba_channel_desc& cd = d.chans[ci];
     const int R = e->wave_rate, N = e->fft_size;
     memset(&k, 0, sizeof(k));
     memset(&st, 0, sizeof(st));
@@ -309,7 +334,7 @@ int setup_channel(ba_engine* e, Dev& d, int ci, ba::K2Chan& k, ba::K2State& st, 
     k.modulation = cd.modulation;
     k.afc = cd.afc & 0xff;
     k.has_iq_outputs = cd.has_iq_outputs ? 1 : 0;
-    k.needs_raw_iq = (cd.modulation == BA_MOD_NFM || cd.bandwidth != 0 || cd.has_iq_outputs) ? 1 : 0; /* config.cpp:162,596,674-680 */
+    k.needs_raw_iq = needs_raw_iq;
     k.fm_demod = e->fm_demod;
     k.ampfactor = cd.ampfactor;
     float alpha = model::alpha_default(R);
@@ -349,10 +374,10 @@ int setup_channel(ba_engine* e, Dev& d, int ci, ba::K2Chan& k, ba::K2State& st, 
             k.lp_c0 = yc[0], k.lp_c1 = yc[1], k.lp_gain = gain;
         }
     }
-    k.base_bin = model::bin_index(cd.frequency, d.cfg.sample_rate, d.cfg.centerfreq, N);
+    k.base_bin = model::bin_index(frequency0, d.cfg.sample_rate, d.cfg.centerfreq, N);
     d.base_bins[ci] = k.base_bin;
     if (k.needs_raw_iq)
-        k.dm_dphi = model::derotation_step(cd.frequency, d.cfg.centerfreq, d.cfg.sample_rate, R);
+        k.dm_dphi = model::derotation_step(frequency0, d.cfg.centerfreq, d.cfg.sample_rate, R);
     if (cd.ctcss > 0) { /* Squelch::set_ctcss_freq, squelch.cpp:106-116 */
         K2Ctcss& c = ctcss_pool[n_ctcss];
         memset(&c, 0, sizeof(c));
@@ -447,9 +472,9 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
     if (!desc || !out)
         return fail(BA_ERR_BAD_ARG, "null argument");
     *out = nullptr;
-    if (desc->abi_version != 1 && desc->abi_version != BA_CUDA_ABI_VERSION)
-        return fail(BA_ERR_BAD_ARG, "ABI version %d, library speaks 1..%d", desc->abi_version, BA_CUDA_ABI_VERSION);
-    const int n_mixers = desc->abi_version >= 2 ? desc->mixer_count : 0; /* version 1 descriptors end before the mixer fields */
+    if (desc->abi_version != BA_CUDA_ABI_VERSION)
+        return fail(BA_ERR_BAD_ARG, "ABI version %d, library speaks %d", desc->abi_version, BA_CUDA_ABI_VERSION);
+    const int n_mixers = desc->mixer_count;
     if (n_mixers < 0 || (n_mixers > 0 && !desc->mixers))
         return fail(BA_ERR_BAD_ARG, "mixer_count %d without mixers", n_mixers);
     const int N = desc->fft_size;
@@ -536,6 +561,17 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
         d->cfg = dd;
         d->chans.assign(dd.channels, dd.channels + dd.channel_count);
         d->cfg.channels = nullptr;
+        for (ba_channel_desc& c : d->chans) { /* freqlist: named in scan mode, else the channel's own fields (mk_freqlist(1)) */
+            if (c.freq_count < 0 || (c.freq_count > 0 && !c.freqs))
+                return fail(BA_ERR_BAD_ARG, "device %d: freq_count %d without freqs", di, c.freq_count);
+            if (c.freq_count > 0)
+                d->freqs.emplace_back(c.freqs, c.freqs + c.freq_count);
+            else
+                d->freqs.emplace_back(1, ba_freq_desc{c.frequency, c.modulation, c.ampfactor, c.squelch_threshold_dbfs, c.squelch_snr_threshold, c.notch, c.notch_q, c.ctcss, c.bandwidth});
+            c.freqs = nullptr;
+        }
+        d->freq_idx.assign(dd.channel_count, 0);
+        d->bank0.assign(dd.channel_count, SIZE_MAX);
         d->C = dd.channel_count;
         d->c_pad = (d->C + 3) & ~3;
         d->sample_bytes = 2 * (size_t)dd.bytes_per_sample;
@@ -544,15 +580,18 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
         d->first_chan = e->total_channels;
         e->total_channels += d->C;
         e->max_channels = std::max(e->max_channels, d->C);
-        for (const ba_channel_desc& c : d->chans) {
+        for (size_t ci = 0; ci < d->chans.size(); ci++) {
+            const ba_channel_desc& c = d->chans[ci];
             if (c.afc & 0xff)
                 d->any_afc = true;
             if (c.has_iq_outputs)
-                d->any_iq = true;
-            if (c.modulation == BA_MOD_NFM || c.bandwidth != 0 || c.has_iq_outputs) /* needs_raw_iq, config.cpp:162,596,674-680 */
-                d->any_raw = true;
-            if (c.ctcss > 0)
-                n_ctcss++;
+                d->any_iq = d->any_raw = true;
+            for (const ba_freq_desc& f : d->freqs[ci]) {
+                if (f.modulation == BA_MOD_NFM || f.bandwidth != 0) /* needs_raw_iq, config.cpp:162,596,674-680 */
+                    d->any_raw = true;
+                if (f.ctcss > 0)
+                    n_ctcss++;
+            }
         }
         e->any_afc |= d->any_afc;
         e->any_iq |= d->any_iq;
@@ -598,14 +637,37 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
     CU(cudaMalloc((void**)&e->d_order, sizeof(int32_t) * TC));
     CU(cudaMalloc((void**)&e->d_tile_counter, sizeof(uint32_t)));
     int used_ctcss = 0;
+    std::vector<K2Chan> bank_chan; /* scan channels: constants and initial state of every frequency, in list order */
+    std::vector<K2State> bank_state;
     for (size_t di = 0; di < e->dev.size(); di++) {
         Dev& d = *e->dev[di];
         for (int ci = 0; ci < d.C; ci++) {
             const int gi = d.first_chan + ci;
-            int rc = setup_channel(e, d, ci, e->h_chan[gi], h_state[gi], h_ctcss.data(), used_ctcss, e->info[gi]);
+            const std::vector<ba_freq_desc>& fl = d.freqs[ci];
+            int raw = d.chans[ci].has_iq_outputs ? 1 : 0;
+            for (const ba_freq_desc& f : fl)
+                if (f.modulation == BA_MOD_NFM || f.bandwidth != 0)
+                    raw = 1;
+            int rc = setup_channel(e, d, ci, with_freq(d.chans[ci], fl[0]), fl[0].frequency, raw, e->h_chan[gi], h_state[gi], h_ctcss.data(), used_ctcss, e->info[gi]);
             if (rc != BA_OK)
                 return rc;
             e->h_chan[gi].dev = (int32_t)di;
+            if (fl.size() > 1) {
+                d.bank0[ci] = bank_chan.size();
+                bank_chan.push_back(e->h_chan[gi]);
+                bank_state.push_back(h_state[gi]);
+                for (size_t f = 1; f < fl.size(); f++) {
+                    K2Chan k;
+                    K2State st;
+                    ba_channel_info unused;
+                    rc = setup_channel(e, d, ci, with_freq(d.chans[ci], fl[f]), fl[0].frequency, raw, k, st, h_ctcss.data(), used_ctcss, unused);
+                    if (rc != BA_OK)
+                        return rc;
+                    k.dev = (int32_t)di;
+                    bank_chan.push_back(k);
+                    bank_state.push_back(st);
+                }
+            }
         }
         std::vector<uint32_t> bins(d.c_pad, 0);
         std::copy(d.base_bins.begin(), d.base_bins.end(), bins.begin());
@@ -619,6 +681,9 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
             order[i] = i;
         auto plain = [&](int i) {
             const K2Chan& k = e->h_chan[i];
+            const Dev& dv = *e->dev[k.dev];
+            if (dv.freqs[k.col].size() > 1) /* a scan channel changes kind with its frequency: the general kernel reads the options at run time */
+                return false;
             return k.modulation == BA_MOD_AM && !k.needs_raw_iq && !k.notch_on && !k.ctcss && !k.has_iq_outputs && !k.afc && !(e->flags & BA_FLAG_TRACE);
         };
         auto kind = [&](int i) {
@@ -634,6 +699,12 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
     CU(cudaMemcpy(e->d_chan, e->h_chan.data(), sizeof(K2Chan) * TC, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(e->d_state, h_state.data(), sizeof(K2State) * TC, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(e->d_ctcss, h_ctcss.data(), sizeof(K2Ctcss) * std::max(1, n_ctcss), cudaMemcpyHostToDevice));
+    if (!bank_chan.empty()) {
+        CU(cudaMalloc((void**)&e->d_bank_chan, sizeof(K2Chan) * bank_chan.size()));
+        CU(cudaMalloc((void**)&e->d_bank_state, sizeof(K2State) * bank_state.size()));
+        CU(cudaMemcpy(e->d_bank_chan, bank_chan.data(), sizeof(K2Chan) * bank_chan.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(e->d_bank_state, bank_state.data(), sizeof(K2State) * bank_state.size(), cudaMemcpyHostToDevice));
+    }
 
     /* output arenas, two slots */
     {
@@ -1364,6 +1435,29 @@ int ba_cuda_mixer_input_mask(ba_engine* e, int mixer, int input, int enabled) {
     if (enabled && !mi.enabled) /* the batches it delivered while masked were never parked; the reference has no re-enable either */
         return fail(BA_ERR_STATE, "mixer %d input %d was disabled and cannot be re-enabled", mixer, input);
     mi.enabled = enabled != 0;
+    return BA_OK;
+}
+
+int ba_cuda_set_freq_idx(ba_engine* e, int dev, int channel, int freq_idx, uint64_t* from_batch) {
+    Dev* d = get_dev(e, dev);
+    if (!d)
+        return BA_ERR_BAD_ARG;
+    if (channel < 0 || channel >= d->C || freq_idx < 0 || freq_idx >= (int)d->freqs[channel].size())
+        return fail(BA_ERR_BAD_ARG, "input %d channel %d has no frequency %d", dev, channel, freq_idx);
+    if (from_batch)
+        *from_batch = d->batches_done;
+    const int old = d->freq_idx[channel];
+    if (old == freq_idx)
+        return BA_OK;
+    /* behind every demodulator launch queued so far, ahead of the next one: park the freq_t state of `old`, bring in `freq_idx` */
+    cudaStream_t k2s = e->any_afc ? e->s_k : e->s_k2;
+    const size_t b0 = d->bank0[channel];
+    const int gi = d->first_chan + channel;
+    int rc = ba::k2_scan_switch_launch(e->d_chan + gi, e->d_state + gi, e->d_bank_chan + b0, e->d_bank_state + b0, old, freq_idx, k2s);
+    if (rc != 0)
+        return fail(BA_ERR_CUDA, "scan switch launch: %s", cudaGetErrorString((cudaError_t)rc));
+    e->launches++;
+    d->freq_idx[channel] = freq_idx;
     return BA_OK;
 }
 

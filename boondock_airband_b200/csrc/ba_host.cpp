@@ -505,8 +505,10 @@ int anynum2int(const Node& n) {
 struct DeviceModel {
     ba_device_desc desc{};
     std::vector<ba_channel_desc> channels;
+    std::vector<std::vector<ba_freq_desc>> freq_lists; /* per channel; empty in multichannel mode */
     std::vector<int> source_index;
     std::vector<std::pair<std::string, std::string>> settings;
+    bool scan = false;
 };
 
 }  // namespace
@@ -587,8 +589,10 @@ int scan_outputs(ba_conf& c, const Node& outs, int i, int j, int dev_index, int 
     return enabled;
 }
 
-/* parse_channels(), config.cpp:312-729, multichannel mode; R = WAVE_RATE of the build being modelled */
-void translate_channels(ba_conf& c, const Node& chans, DeviceModel& dev, int i, int R) {
+/* parse_channels(), config.cpp:312-729, both modes; R = WAVE_RATE of the build being modelled.  A channel is translated
+ * into its frequency list fl[0..freq_count) (one entry in multichannel mode, "freqs" in scan mode) exactly as the
+ * reference fills channel->freqlist[f]; the ba_channel_desc carries fl[0] in its own fields and, in scan mode, the list. */
+void translate_channels(ba_conf& c, const Node& chans, DeviceModel& dev, int i, int R, bool scan, int fft_size) {
     const bool nfm_build = R == 16000;
     bool slot_needs_raw_iq = false; /* channel_t.needs_raw_iq of slot jj survives a dropped channel (the slot is calloc'ed once) */
     for (int j = 0; j < chans.length(); j++) {
@@ -596,66 +600,112 @@ void translate_channels(ba_conf& c, const Node& chans, DeviceModel& dev, int i, 
         if (disabled(ch))
             continue;
         ba_channel_desc d{};
-        d.ampfactor = 1.0f;             /* mk_freqlist, config.cpp:281 */
-        d.squelch_snr_threshold = -1.f; /* keep Squelch's default */
         d.tau_us = -1;
         const int highpass = ch.exists("highpass") ? ch.at("highpass").as_int() : 100;
         const int lowpass = ch.exists("lowpass") ? ch.at("lowpass").as_int() : 2500;
         if (lowpass > 0 && lowpass < highpass)
             raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: lowpass (%d) must be greater than or equal to highpass (%d)", i, j, lowpass, highpass);
-        d.modulation = BA_MOD_AM;
+        int channel_modulation = BA_MOD_AM;
         if (ch.exists("modulation")) {
             const char* m = ch.at("modulation").as_cstr();
             if (nfm_build && !strncmp(m, "nfm", 3))
-                d.modulation = BA_MOD_NFM;
+                channel_modulation = BA_MOD_NFM;
             else if (strncmp(m, "am", 2) != 0)
                 raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: unknown modulation", i, j);
         }
         d.afc = ch.exists("afc") ? (int)(unsigned char)ch.at("afc").as_uint() : 0;
-        d.frequency = anynum2int(ch.at("freq"));
-        { /* warn_if_freq_not_in_range, config.cpp:289-296 */
+        std::vector<ba_freq_desc> fl;
+        auto fresh = [&](int frequency, int modulation) { /* mk_freqlist, config.cpp:268-287 */
+            ba_freq_desc f{};
+            f.frequency = frequency;
+            f.modulation = modulation;
+            f.ampfactor = 1.0f;
+            f.squelch_snr_threshold = -1.f; /* keep Squelch's default */
+            return f;
+        };
+        if (!scan) {
+            fl.push_back(fresh(anynum2int(ch.at("freq")), channel_modulation));
+            /* warn_if_freq_not_in_range, config.cpp:289-296 */
             const float bw_limit = (float)dev.desc.sample_rate / 2.f * 0.9f;
-            if ((float)abs(d.frequency - dev.desc.centerfreq) >= bw_limit)
-                warn(c, "Warning: dev[%d].channel[%d]: frequency %.3f MHz is outside of SDR operating bandwidth (%.3f-%.3f MHz)", i, j, (double)d.frequency / 1e6,
+            if ((float)abs(fl[0].frequency - dev.desc.centerfreq) >= bw_limit)
+                warn(c, "Warning: dev[%d].channel[%d]: frequency %.3f MHz is outside of SDR operating bandwidth (%.3f-%.3f MHz)", i, j, (double)fl[0].frequency / 1e6,
                      (double)(dev.desc.centerfreq - bw_limit) / 1e6, (double)(dev.desc.centerfreq + bw_limit) / 1e6);
+            if (ch.exists("label"))
+                (void)ch.at("label").as_cstr();
+        } else { /* R_SCAN, config.cpp:364-433 */
+            const Node& freqs = ch.at("freqs");
+            const int n = freqs.length();
+            if (n < 1)
+                raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: freqs should be a list with at least one element", i, j);
+            if (ch.exists("labels") && ch.at("labels").length() < n)
+                raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: labels should be a list with at least %d elements", i, j, n);
+            struct {
+                const char* key;
+                const char* what;
+            } lists[] = {{"squelch_threshold", "squelch_threshold should be an int or a list of ints"},
+                         {"squelch_snr_threshold", "squelch_snr_threshold should be an int, a float or a list of ints or floats"},
+                         {"notch", "notch should be an float or a list of floats"},
+                         {"notch_q", "notch_q should be a float or a list of floats"},
+                         {"ctcss", "ctcss should be an float or a list of floats"}};
+            for (auto& l : lists)
+                if (ch.exists(l.key) && ch.at(l.key).kind == conf::K_LIST && ch.at(l.key).length() < n)
+                    raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: %s with at least %d elements", i, j, l.what, n);
+            if (ch.exists("modulation") && ch.exists("modulations"))
+                raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: can't set both modulation and modulations", i, j);
+            if (ch.exists("modulations") && ch.at("modulations").length() < n)
+                raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: modulations should be a list with at least %d elements", i, j, n);
+            for (int f = 0; f < n; f++) {
+                int mod = channel_modulation;
+                if (ch.exists("labels"))
+                    (void)ch.at("labels").at(f).as_cstr();
+                if (ch.exists("modulations")) {
+                    const char* m = ch.at("modulations").at(f).as_cstr();
+                    if (nfm_build && !strncmp(m, "nfm", 3))
+                        mod = BA_MOD_NFM;
+                    else if (!strncmp(m, "am", 2))
+                        mod = BA_MOD_AM;
+                    else
+                        raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d] modulations.[%d]: unknown modulation", i, j, f);
+                }
+                fl.push_back(fresh(anynum2int(freqs.at(f)), mod));
+            }
+            /* "We tune 20 FFT bins higher to avoid DC spike" (config.cpp:429-431): int + 20 * (double)(int / size_t), stored in an int */
+            dev.desc.centerfreq = (int)(fl[0].frequency + 20 * (double)((size_t)dev.desc.sample_rate / (size_t)fft_size));
         }
-        if (ch.exists("label"))
-            (void)ch.at("label").as_cstr();
+        const int n = (int)fl.size();
         if (ch.exists("squelch"))
             warn(c, "Warning: 'squelch' no longer supported and will be ignored, use 'squelch_threshold' or 'squelch_snr_threshold' instead");
         if (ch.exists("squelch_threshold") && ch.exists("squelch_snr_threshold"))
             warn(c, "Warning: Both 'squelch_threshold' and 'squelch_snr_threshold' are set and may conflict");
         if (ch.exists("squelch_threshold")) {
             const Node& t = ch.at("squelch_threshold");
-            int dbfs;
-            if (t.kind == conf::K_LIST)
-                dbfs = t.at(0).as_int();
-            else if (t.kind == conf::K_INT)
-                dbfs = (int)t.i;
-            else
+            if (t.kind != conf::K_LIST && t.kind != conf::K_INT)
                 raise(BA_HOST_ERR_CONFIG, "Invalid value for squelch_threshold (should be int or list - use parentheses)");
-            if (dbfs > 0)
-                raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: squelch_threshold must be less than or equal to 0", i, j);
-            d.squelch_threshold_dbfs = dbfs;
+            for (int f = 0; f < n; f++) {
+                const int dbfs = t.kind == conf::K_LIST ? t.at(f).as_int() : (int)t.i;
+                if (dbfs > 0)
+                    raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: squelch_threshold must be less than or equal to 0", i, j);
+                fl[f].squelch_threshold_dbfs = dbfs;
+            }
         }
         bool dropped = false;
         if (ch.exists("squelch_snr_threshold")) {
             const Node& t = ch.at("squelch_snr_threshold");
             if (t.kind == conf::K_LIST) {
-                const Node& e = t.at(0);
-                float snr = 0.f;
-                if (e.kind == conf::K_FLOAT)
-                    snr = (float)e.f;
-                else if (e.kind == conf::K_INT)
-                    snr = (float)(int)e.i;
-                else
-                    raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: squelch_snr_threshold list must be of int or float", i, j);
-                if (snr == -1.0f) {
-                    /* "disable" for this frequency: the default stays */
-                } else if (snr < 0) {
-                    raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: squelch_snr_threshold must be greater than or equal to 0", i, j);
-                } else {
-                    d.squelch_snr_threshold = snr;
+                for (int f = 0; f < n; f++) {
+                    const Node& e = t.at(f);
+                    float snr = 0.f;
+                    if (e.kind == conf::K_FLOAT)
+                        snr = (float)e.f;
+                    else if (e.kind == conf::K_INT)
+                        snr = (float)(int)e.i;
+                    else
+                        raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: squelch_snr_threshold list must be of int or float", i, j);
+                    if (snr == -1.0f)
+                        continue; /* "disable" for this frequency: the default stays */
+                    if (snr < 0)
+                        raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: squelch_snr_threshold must be greater than or equal to 0", i, j);
+                    fl[f].squelch_snr_threshold = snr;
                 }
             } else if (t.kind == conf::K_FLOAT || t.kind == conf::K_INT) {
                 const float snr = t.kind == conf::K_FLOAT ? (float)t.f : (float)(int)t.i;
@@ -664,7 +714,8 @@ void translate_channels(ba_conf& c, const Node& chans, DeviceModel& dev, int i, 
                 } else if (snr < 0) {
                     raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: squelch_snr_threshold must be greater than or equal to 0", i, j);
                 } else {
-                    d.squelch_snr_threshold = snr;
+                    for (int f = 0; f < n; f++)
+                        fl[f].squelch_snr_threshold = snr;
                 }
             } else {
                 raise(BA_HOST_ERR_CONFIG, "Invalid value for squelch_snr_threshold (should be float, int, or list of int/float - use parentheses)");
@@ -678,70 +729,89 @@ void translate_channels(ba_conf& c, const Node& chans, DeviceModel& dev, int i, 
             const Node& t = ch.at("notch");
             const Node* q = ch.find("notch_q");
             if (q && q->kind != t.kind)
-                raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: notch_q (if set) must be the same type as notch - float or a list of floats with at least 1 elements", i,
-                      j);
+                raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: notch_q (if set) must be the same type as notch - float or a list of floats with at least %d elements",
+                      i, j, n);
             if (t.kind == conf::K_LIST) {
-                const float freq = t.at(0).as_float();
-                float qq = q ? q->at(0).as_float() : 10.0f;
-                if (qq == 0.0f)
-                    qq = 10.0f;
-                else if (qq <= 0.0f)
-                    raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d] freq.[0]: invalid value for notch_q: %g (must be greater than 0.0)", i, j, qq);
-                if (freq < 0)
-                    warn(c, "devices.[%d] channels.[%d] freq.[0]: invalid value for notch: %g, ignoring", i, j, freq);
-                else if (freq > 0) {
-                    d.notch = freq;
-                    d.notch_q = qq;
+                for (int f = 0; f < n; f++) {
+                    const float freq = t.at(f).as_float();
+                    float qq = q ? q->at(f).as_float() : 10.0f;
+                    if (qq == 0.0f)
+                        qq = 10.0f;
+                    else if (qq <= 0.0f)
+                        raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d] freq.[%d]: invalid value for notch_q: %g (must be greater than 0.0)", i, j, f, qq);
+                    if (freq < 0) {
+                        warn(c, "devices.[%d] channels.[%d] freq.[%d]: invalid value for notch: %g, ignoring", i, j, f, freq);
+                    } else if (freq > 0) {
+                        fl[f].notch = freq;
+                        fl[f].notch_q = qq;
+                    }
                 }
             } else if (t.kind == conf::K_FLOAT) {
                 const float freq = (float)t.f;
                 const float qq = q ? q->as_float() : 10.0f;
                 if (qq <= 0.0f)
                     raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: invalid value for notch_q: %g (must be greater than 0.0)", i, j, qq);
-                if (freq < 0)
-                    warn(c, "devices.[%d] channels.[%d]: notch value '%g' invalid, ignoring", i, j, freq);
-                else if (freq > 0) {
-                    d.notch = freq;
-                    d.notch_q = qq;
+                for (int f = 0; f < n; f++) {
+                    if (freq < 0) {
+                        warn(c, "devices.[%d] channels.[%d]: notch value '%g' invalid, ignoring", i, j, freq);
+                    } else if (freq > 0) {
+                        fl[f].notch = freq;
+                        fl[f].notch_q = qq;
+                    }
                 }
             } else {
-                raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: notch should be an float or a list of floats with at least 1 elements", i, j);
+                raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: notch should be an float or a list of floats with at least %d elements", i, j, n);
             }
         }
         if (ch.exists("ctcss")) {
             const Node& t = ch.at("ctcss");
-            float freq;
-            if (t.kind == conf::K_LIST)
-                freq = t.at(0).as_float();
-            else if (t.kind == conf::K_FLOAT)
-                freq = (float)t.f;
-            else
-                raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: ctcss should be an float or a list of floats with at least 1 elements", i, j);
-            if (freq < 0 || (freq == 0 && t.kind == conf::K_FLOAT))
-                warn(c, "devices.[%d] channels.[%d]: ctcss value '%g' invalid, ignoring", i, j, freq);
-            else if (freq > 0)
-                d.ctcss = freq;
+            if (t.kind != conf::K_LIST && t.kind != conf::K_FLOAT)
+                raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: ctcss should be an float or a list of floats with at least %d elements", i, j, n);
+            for (int f = 0; f < n; f++) {
+                const float freq = t.kind == conf::K_LIST ? t.at(f).as_float() : (float)t.f;
+                if (freq < 0 || (freq == 0 && t.kind == conf::K_FLOAT)) {
+                    if (t.kind == conf::K_LIST)
+                        warn(c, "devices.[%d] channels.[%d] freq.[%d]: invalid value for ctcss: %g, ignoring", i, j, f, freq);
+                    else
+                        warn(c, "devices.[%d] channels.[%d]: ctcss value '%g' invalid, ignoring", i, j, freq);
+                } else if (freq > 0) {
+                    fl[f].ctcss = freq;
+                }
+            }
         }
         bool needs_raw_iq = slot_needs_raw_iq;
         if (ch.exists("bandwidth")) {
             needs_raw_iq = slot_needs_raw_iq = true;
             const Node& t = ch.at("bandwidth");
-            const int bw = anynum2int(t.kind == conf::K_LIST ? t.at(0) : t);
-            if (bw == 0 && t.kind != conf::K_LIST) {
-                warn(c, "Note: devices.[%d] channels.[%d] is dropped without a message by the reference (bandwidth = 0, config.cpp:612-614)", i, j);
-                continue;
+            if (t.kind == conf::K_LIST) {
+                for (int f = 0; f < n; f++) {
+                    const int bw = anynum2int(t.at(f));
+                    if (bw < 0)
+                        warn(c, "devices.[%d] channels.[%d] freq.[%d]: bandwidth value '%d' invalid, ignoring", i, j, f, bw);
+                    else
+                        fl[f].bandwidth = bw; /* 0: "disable" for this frequency */
+                }
+            } else {
+                const int bw = anynum2int(t);
+                if (bw == 0) {
+                    warn(c, "Note: devices.[%d] channels.[%d] is dropped without a message by the reference (bandwidth = 0, config.cpp:612-614)", i, j);
+                    continue;
+                }
+                if (bw < 0)
+                    warn(c, "devices.[%d] channels.[%d]: bandwidth value '%d' invalid, ignoring", i, j, bw);
+                else
+                    for (int f = 0; f < n; f++)
+                        fl[f].bandwidth = bw;
             }
-            if (bw < 0)
-                warn(c, "devices.[%d] channels.[%d]: bandwidth value '%d' invalid, ignoring", i, j, bw);
-            else
-                d.bandwidth = bw;
         }
         if (ch.exists("ampfactor")) {
             const Node& t = ch.at("ampfactor");
-            const float a = t.kind == conf::K_LIST ? t.at(0).as_float() : t.as_float();
-            if (a < 0)
-                raise(BA_HOST_ERR_CONFIG, "devices.[%d] channels.[%d]: ampfactor '%g' must not be negative", i, j, a);
-            d.ampfactor = a;
+            for (int f = 0; f < n; f++) {
+                const float a = t.kind == conf::K_LIST ? t.at(f).as_float() : t.as_float();
+                if (a < 0)
+                    raise(BA_HOST_ERR_CONFIG, "devices.[%d] channels.[%d]: ampfactor '%g' must not be negative", i, j, a);
+                fl[f].ampfactor = a;
+            }
         }
         if (nfm_build && ch.exists("tau"))
             d.tau_us = ch.at("tau").as_int();
@@ -750,11 +820,29 @@ void translate_channels(ba_conf& c, const Node& chans, DeviceModel& dev, int i, 
         if (outs.length() < 1 || scan_outputs(c, outs, i, j, (int)c.devs.size(), (int)dev.channels.size(), &has_iq) < 1)
             raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d] channels.[%d]: no outputs defined", i, j);
         d.has_iq_outputs = has_iq ? 1 : 0;
-        /* needs_raw_iq without a low-pass (bandwidth present but rejected, or inherited from a dropped entry's slot):
-         * expressed as bandwidth < 0, which the engine reads as "raw IQ path on, no filter" */
-        if (needs_raw_iq && d.bandwidth == 0 && d.modulation != BA_MOD_NFM && !has_iq)
-            d.bandwidth = -1;
+        /* needs_raw_iq without a low-pass anywhere (bandwidth present but rejected or zero in every list entry, or inherited from a
+         * dropped entry's slot): expressed as bandwidth < 0 on the first frequency, which the engine reads as "raw IQ path on, no filter" */
+        bool implied = has_iq;
+        for (const ba_freq_desc& f : fl)
+            implied = implied || f.modulation == BA_MOD_NFM || f.bandwidth != 0;
+        if (needs_raw_iq && !implied)
+            fl[0].bandwidth = -1;
         slot_needs_raw_iq = false; /* the next slot is fresh */
+        d.frequency = fl[0].frequency;
+        d.modulation = fl[0].modulation;
+        d.ampfactor = fl[0].ampfactor;
+        d.squelch_threshold_dbfs = fl[0].squelch_threshold_dbfs;
+        d.squelch_snr_threshold = fl[0].squelch_snr_threshold;
+        d.notch = fl[0].notch;
+        d.notch_q = fl[0].notch_q;
+        d.ctcss = fl[0].ctcss;
+        d.bandwidth = fl[0].bandwidth;
+        if (scan) {
+            dev.freq_lists.push_back(fl); /* pointers are set once the device is complete */
+            d.freq_count = n;
+        } else {
+            dev.freq_lists.emplace_back();
+        }
         dev.channels.push_back(d);
         dev.source_index.push_back(j);
     }
@@ -901,16 +989,18 @@ void translate(ba_conf& c, const Node& root, int wave_rate) {
                 raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d]: sample_rate must be greater than %d", i, R);
             d.sample_rate = sr;
         }
+        bool scan = false; /* R_SCAN / R_MULTICHANNEL, config.cpp:761-772 */
         if (dn.exists("mode")) {
             const char* m = dn.at("mode").as_cstr();
             if (!strncmp(m, "multichannel", 12)) {
             } else if (!strncmp(m, "scan", 4)) {
-                raise(BA_HOST_ERR_UNSUPPORTED, "devices.[%d]: scan mode is outside this engine (SURVEY.md section 8, row f-3)", i);
+                scan = true;
             } else {
                 raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d]: invalid mode (must be one of: \"scan\", \"multichannel\")", i);
             }
         }
-        d.centerfreq = anynum2int(dn.at("centerfreq"));
+        if (!scan) /* in scan mode parse_channels() derives it from the first frequency (config.cpp:773-775,429-431) */
+            d.centerfreq = anynum2int(dn.at("centerfreq"));
         d.tau_us = global_tau;
         if (nfm_build && dn.exists("tau"))
             d.tau_us = dn.at("tau").as_int();
@@ -962,14 +1052,19 @@ void translate(ba_conf& c, const Node& root, int wave_rate) {
         const Node& chans = dn.at("channels");
         if (chans.length() < 1)
             raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d]: no channels configured", i);
-        translate_channels(c, chans, *dev, i, R);
+        translate_channels(c, chans, *dev, i, R, scan, fft_size);
         if (dev->channels.empty())
             raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d]: no channels enabled", i);
+        if (scan && dev->channels.size() > 1)
+            raise(BA_HOST_ERR_CONFIG, "Configuration error: devices.[%d]: only one channel is allowed in scan mode", i);
+        dev->scan = scan;
         c.devs.push_back(std::move(dev));
     }
     if (c.devs.empty())
         raise(BA_HOST_ERR_CONFIG, "Configuration error: no devices defined");
     for (auto& dev : c.devs) {
+        for (size_t k = 0; k < dev->channels.size(); k++)
+            dev->channels[k].freqs = dev->freq_lists[k].empty() ? nullptr : dev->freq_lists[k].data();
         dev->desc.channel_count = (int32_t)dev->channels.size();
         dev->desc.channels = dev->channels.data();
         c.dev_descs.push_back(dev->desc);
@@ -1047,6 +1142,36 @@ const char* ba_conf_device_setting(const ba_conf* c, int device, const char* key
 
 const char* ba_conf_mixer_name(const ba_conf* c, int mixer) {
     return c && mixer >= 0 && mixer < (int)c->mixers.size() ? c->mixers[mixer].name.c_str() : nullptr;
+}
+
+int ba_conf_device_is_scan(const ba_conf* c, int device) {
+    return c && device >= 0 && device < (int)c->devs.size() && c->devs[device]->scan ? 1 : 0;
+}
+
+/* controller_thread(), boondock_airband.cpp:101-139, as a step function: one call per 200 ms poll.  state = {i,
+ * consecutive_squelch_off, last_frequency, freq_count}.  Returns the freq_idx the channel is on after the poll (hand it to
+ * ba_cuda_set_freq_idx and retune the input when it changed); *tag_freq (optional) is set to i when the reference would
+ * queue a tag for the outputs' metadata (squelch just opened on a new frequency), else -1. */
+int ba_scan_controller_poll(int32_t state[4], int has_signal, int* tag_freq) {
+    if (tag_freq)
+        *tag_freq = -1;
+    if (!state || state[3] < 2)
+        return state ? state[0] : 0;
+    if (!has_signal) { /* axcindicate == NO_SIGNAL */
+        if (state[1] < 10) {
+            state[1]++;
+        } else {
+            state[0] = (state[0] + 1) % state[3];
+        }
+    } else {
+        if (state[1] == 10 && state[0] != state[2]) {
+            if (tag_freq)
+                *tag_freq = state[0];
+            state[2] = state[0];
+        }
+        state[1] = 0;
+    }
+    return state[0];
 }
 
 int ba_conf_multiple_demod_threads(const ba_conf* c) { return c ? c->multiple_demod_threads : 0; }

@@ -27,7 +27,7 @@ _LIBS = {}
 SYMBOLS = (
     "ba_cuda_create", "ba_cuda_destroy", "ba_cuda_last_error", "ba_cuda_visible_devices", "ba_cuda_input_ring",
     "ba_cuda_submit", "ba_cuda_input_space", "ba_cuda_commit", "ba_cuda_submit_external", "ba_cuda_attach_device_stream",
-    "ba_cuda_advance_device_stream", "ba_cuda_process", "ba_cuda_collect", "ba_cuda_collect_mixer", "ba_cuda_mixer_input_mask", "ba_cuda_ticket_ms", "ba_cuda_step_bytes",
+    "ba_cuda_advance_device_stream", "ba_cuda_process", "ba_cuda_collect", "ba_cuda_collect_mixer", "ba_cuda_mixer_input_mask", "ba_cuda_set_freq_idx", "ba_cuda_ticket_ms", "ba_cuda_step_bytes",
     "ba_cuda_channel_info", "ba_cuda_window", "ba_cuda_debug_frames", "ba_cuda_debug_picks",
     "ba_cuda_debug_inject_picks", "ba_cuda_launch_count", "ba_cuda_kernel_ms", "ba_cuda_copy_ms", "ba_cuda_mark", "ba_cuda_mark_ms",
 )
@@ -72,6 +72,7 @@ def load_library(path: Optional[str] = None):
     L.ba_cuda_input_space.argtypes = [vp, C.c_int, C.POINTER(C.c_size_t)]
     L.ba_cuda_collect_mixer.argtypes = [vp, C.c_int, C.c_int, C.POINTER(abi.MixerOut)]
     L.ba_cuda_mixer_input_mask.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.ba_cuda_set_freq_idx.argtypes = [vp, C.c_int, C.c_int, C.c_int, u64p]
     L.ba_cuda_launch_count.argtypes = [vp, u64p]
     L.ba_cuda_kernel_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     L.ba_cuda_copy_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
@@ -202,6 +203,12 @@ class Engine:
 
     def mixer_input_mask(self, mixer: int, input: int, enabled: bool):
         self._check("ba_cuda_mixer_input_mask", self.L.ba_cuda_mixer_input_mask(self.h, mixer, input, 1 if enabled else 0))
+
+    def set_freq_idx(self, dev: int, channel: int, freq_idx: int) -> int:
+        """Scan mode: switch the channel to freqlist[freq_idx] from the next process() on; returns the first batch it applies to."""
+        b = C.c_uint64()
+        self._check("ba_cuda_set_freq_idx", self.L.ba_cuda_set_freq_idx(self.h, dev, channel, freq_idx, C.byref(b)))
+        return b.value
 
     def ticket_ms(self, ticket: int) -> float:
         ms = C.c_float()

@@ -23,11 +23,11 @@ INPUT_UNKNOWN, INPUT_INITIALIZED, INPUT_RUNNING, INPUT_FAILED, INPUT_STOPPED = r
 # every symbol include/ba_host.h declares
 SYMBOLS = (
     "ba_conf_parse_file", "ba_conf_parse_text", "ba_conf_free", "ba_host_last_error", "ba_conf_engine_desc",
-    "ba_conf_device_count", "ba_conf_device_setting", "ba_conf_mixer_name", "ba_conf_multiple_demod_threads", "ba_conf_warnings",
+    "ba_conf_device_count", "ba_conf_device_setting", "ba_conf_device_is_scan", "ba_conf_mixer_name", "ba_conf_multiple_demod_threads", "ba_conf_warnings",
     "ba_conf_channel_source_index", "ba_file_input_open", "ba_file_input_start", "ba_file_input_state",
     "ba_file_input_bytes", "ba_file_input_stop", "ba_file_input_sink_for_engine", "ba_file_input_sink_release",
     "ba_handoff_create", "ba_handoff_acquire", "ba_handoff_publish", "ba_handoff_take", "ba_handoff_release", "ba_handoff_close",
-    "ba_handoff_overruns", "ba_handoff_destroy",
+    "ba_handoff_overruns", "ba_handoff_destroy", "ba_scan_controller_poll",
 )
 HANDOFF_TIMEOUT, HANDOFF_CLOSED = -30, -31
 
@@ -72,6 +72,7 @@ def load_library(path: Optional[str] = None):
     L.ba_conf_device_count.argtypes = [vp]
     L.ba_conf_device_setting.argtypes = [vp, C.c_int, C.c_char_p]
     L.ba_conf_device_setting.restype = C.c_char_p
+    L.ba_conf_device_is_scan.argtypes = [vp, C.c_int]
     L.ba_conf_mixer_name.argtypes = [vp, C.c_int]
     L.ba_conf_mixer_name.restype = C.c_char_p
     L.ba_conf_multiple_demod_threads.argtypes = [vp]
@@ -122,7 +123,9 @@ class Config:
                 dev.channels.append(abi.ChannelCfg(
                     freq=c.frequency, modulation=_MOD_NAME[c.modulation], afc=c.afc, ampfactor=c.ampfactor,
                     squelch_threshold=c.squelch_threshold_dbfs, squelch_snr_threshold=c.squelch_snr_threshold, notch=c.notch,
-                    notch_q=c.notch_q, ctcss=c.ctcss, bandwidth=c.bandwidth, tau=c.tau_us, has_iq_outputs=bool(c.has_iq_outputs)))
+                    notch_q=c.notch_q, ctcss=c.ctcss, bandwidth=c.bandwidth, tau=c.tau_us, has_iq_outputs=bool(c.has_iq_outputs),
+                    freqs=[abi.FreqCfg(f.frequency, _MOD_NAME[f.modulation], f.ampfactor, f.squelch_threshold_dbfs, f.squelch_snr_threshold, f.notch,
+                                       f.notch_q, f.ctcss, f.bandwidth) for f in (c.freqs[k] for k in range(c.freq_count))]))
             cfg.devices.append(dev)
         for m in range(d.mixer_count):
             md = d.mixers[m]
@@ -136,6 +139,9 @@ class Config:
     def setting(self, dev: int, key: str) -> Optional[str]:
         v = self._L.ba_conf_device_setting(self._h, dev, key.encode())
         return None if v is None else v.decode()
+
+    def is_scan(self, dev: int) -> bool:
+        return bool(self._L.ba_conf_device_is_scan(self._h, dev))
 
     def source_index(self, dev: int, ch: int) -> int:
         return self._L.ba_conf_channel_source_index(self._h, dev, ch)

@@ -42,7 +42,7 @@ typedef struct ba_conf ba_conf;
 #define BA_HOST_ERR_SYNTAX (-20) /* the text is not in the grammar; ba_host_last_error() names line and column */
 #define BA_HOST_ERR_CONFIG (-21) /* a "Configuration error" of config.cpp (the reference prints it and calls error() = _Exit(1)) */
 #define BA_HOST_ERR_IO (-22)
-#define BA_HOST_ERR_UNSUPPORTED (-23) /* valid for the reference, outside this engine (scan mode) */
+#define BA_HOST_ERR_UNSUPPORTED (-23) /* valid for the reference, outside this engine */
 
 /* wave_rate: 8000 = the reference built without -DNFM, 16000 = with it (boondock_airband.h:67-71); 0 = 16000 when any
  * channel says modulation = "nfm", else 8000.  With 8000 a "nfm" channel is the reference's "unknown modulation" error. */
@@ -58,6 +58,13 @@ BA_HOST_API int ba_conf_device_count(const ba_conf* c);
 /* Settings of the i-th enabled device the input driver reads itself: "type", "filepath", "speedup_factor", "sample_format",
  * "index", "serial", "gain", "device_string", ...  Strings come back as written, numbers formatted with %.17g. NULL if absent. */
 BA_HOST_API const char* ba_conf_device_setting(const ba_conf* c, int device, const char* key);
+/* 1 if the i-th enabled device says mode = "scan" (R_SCAN): one channel whose ba_channel_desc carries the frequency list */
+BA_HOST_API int ba_conf_device_is_scan(const ba_conf* c, int device);
+/* controller_thread() of scan mode (src/boondock_airband.cpp:101-139) as a step function, one call per 200 ms poll of
+ * channels[0].axcindicate.  state = { i, consecutive_squelch_off, last_frequency (start at -1), freq_count }.  Returns the
+ * freq_idx to run next (-> ba_cuda_set_freq_idx + input_set_centerfreq when it changed); *tag_freq (optional) receives i
+ * when the reference queues a metadata tag (tag_queue_put, :131-134), else -1. */
+BA_HOST_API int ba_scan_controller_poll(int32_t state[4], int has_signal, int* tag_freq);
 /* name of the m-th enabled entry of the `mixers` section = ba_engine_desc.mixers[m] (parse_mixers, config.cpp:838-889);
  * its inputs are the channel outputs of type "mixer" naming it, in the order the reference connects them */
 BA_HOST_API const char* ba_conf_mixer_name(const ba_conf* c, int mixer);

@@ -55,6 +55,7 @@ def load(ref: bool = False, fast: bool = False):
     L.ba_oracle_destroy.argtypes = [vp]
     L.ba_oracle_destroy.restype = None
     L.ba_oracle_feed.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.ba_oracle_set_freq_idx.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, C.c_int]
     for n in ("frames", "batches"):
         f = getattr(L, "ba_oracle_" + n)
         f.argtypes = [vp, C.c_int]
@@ -156,6 +157,12 @@ class Oracle:
         arr = (abi.ChannelStatus * n)()
         self.L.ba_oracle_status(self.h, dev, ch, C.cast(arr, C.c_void_p), n)
         return list(arr)
+
+    def set_freq_idx(self, dev, ch, from_batch, freq_idx):
+        """Scan mode: batches >= from_batch of the device run with freqlist[freq_idx] (boondock_airband.cpp:101-139,522)."""
+        rc = self.L.ba_oracle_set_freq_idx(self.h, dev, ch, from_batch, freq_idx)
+        if rc != 0:
+            raise ValueError("ba_oracle_set_freq_idx: %d" % rc)
 
     def channel_info(self, dev, ch) -> abi.ChannelInfo:
         info = abi.ChannelInfo()

@@ -92,6 +92,46 @@ def run_both(cfg: abi.EngineCfg, streams, lib: str, chunk_bytes: int = 1 << 20, 
     return o, res, launches
 
 
+def run_scan(cfg: abi.EngineCfg, streams, lib: str, every: int, order, chunk_bytes: int = 200_000):
+    """Engine: after every `every` batches of device 0 its scan channel moves on through `order` (the controller thread's
+    freq_idx = i, boondock_airband.cpp:115-118).  The oracle gets the same switches at the same batch numbers."""
+    e = Engine(cfg, lib)
+    plan = []
+    try:
+        nd = len(cfg.devices)
+        views = [np.ascontiguousarray(s).view(np.uint8).reshape(-1) for s in streams]
+        pos = [0] * nd
+        acc = e._new_acc()
+        done0, step = 0, 0
+        while True:
+            fed = False
+            for d in range(nd):
+                n = min(chunk_bytes, views[d].size - pos[d], e.input_space(d))
+                if n > 0:
+                    e.submit(d, views[d][pos[d]:pos[d] + n])
+                    pos[d] += n
+                    fed = True
+            produced, advanced = e._step_into(acc)
+            n0 = sum(w.shape[1] for w in acc[0]["waveout"]) // cfg.wave_batch
+            if n0 // every > done0 // every:
+                step += 1
+                idx = order[step % len(order)]
+                plan.append((e.set_freq_idx(0, 0, idx), idx))
+            done0 = n0
+            if not fed and not produced and not advanced:
+                break
+        res = e._finish_acc(acc)
+        launches = e.launch_count()
+    finally:
+        e.close()
+    o = Oracle(cfg)
+    for b, idx in plan:
+        o.set_freq_idx(0, 0, b, idx)
+    for d, s in enumerate(streams):
+        o.feed(d, s)
+    return o, res, plan, launches
+
+
 def check_mixers(cfg: abi.EngineCfg, streams, lib: str, chunk_bytes: int, masked=None):
     """K3 against the restated mixer: bit-exact on the engine's own channel audio (the mixer's arithmetic alone), and within
     the audio tolerance on the oracle's (the whole path)."""

@@ -86,6 +86,27 @@ def mixers_on_multi_device(seconds=0.5):
     return cfg, streams
 
 
+def scan_mode(seconds=1.2):
+    """Row f-3: a scan-mode input (one channel, three frequencies with different freq_t settings: plain AM, NFM through
+    the low-pass with CTCSS and notch, AM with a manual squelch level and gain) next to an ordinary multichannel input.
+    The file does not retune, so every frequency sees the carrier that sits in the channel's bin; what the test
+    exercises is the freq_t switch: each frequency keeps its own Squelch, filters, AGC level and counters."""
+    from boondock_airband_b200.abi import FreqCfg
+    fs, n = 2_560_000, 512
+    f0 = 121_500_000
+    cf = f0 + 20 * (fs // n)  # config.cpp:431: tuned 20 bins above the first frequency
+    scan = ChannelCfg(freq=f0, modulation="nfm", tau=100, freqs=[
+        FreqCfg(f0),
+        FreqCfg(f0 + 25_000, modulation="nfm", bandwidth=12_500, ctcss=100.0, notch=100.0, ampfactor=0.8),
+        FreqCfg(f0 + 50_000, squelch_threshold=-48, ampfactor=1.6, notch=1000.0, notch_q=4.0)])
+    d0 = DeviceCfg(sample_rate=fs, centerfreq=cf, sample_format="u8", channels=[scan])
+    d1 = DeviceCfg(sample_rate=2_400_000, centerfreq=145_000_000, sample_format="s16",
+                   channels=[ChannelCfg(freq=145_000_000 - 300_000), ChannelCfg(freq=145_000_000 + 250_000, modulation="nfm", bandwidth=12_500)])
+    cfg = EngineCfg(fft_size=n, wave_rate=16000, devices=[d0, d1], flags=abi.FLAG_TRACE, max_batches_per_step=1)
+    streams = [synth.synth(d0, seconds, 41, gate_on=0.22, gate_off=0.09), synth.synth(d1, seconds, 42, gate_on=0.3, gate_off=0.1)]
+    return cfg, streams
+
+
 def squelch_steps(levels, fft_size=512):
     """Picked-bin series with constant magnitudes, the stimulus of test_squelch.cpp (0.05 = noise, 0.75 = signal)."""
     z = np.zeros((len(levels), 1, 2), np.float32)

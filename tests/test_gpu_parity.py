@@ -251,3 +251,14 @@ def test_mixer_masked_input(cuda):
     streams[1] = streams[1][: len(streams[1]) // 3]
     mixed, res, _ = parity.check_mixers(cfg, streams, cuda, 400_000, masked={0: [1], 1: [1]})
     assert len(mixed[0]["left"]) > len(res[1]["waveout"][0])
+
+
+@pytest.mark.parametrize("every", [1, 3])
+def test_scan_mode(cuda, every):
+    """Row f-3: scan mode on the GPU - the freq_t of the channel is switched between batches (ba_cuda_set_freq_idx)."""
+    cfg, streams = scenarios.scan_mode(3.0)
+    o, res, plan, launches = parity.run_scan(cfg, streams, cuda, every=every, order=[0, 1, 2, 1, 0, 2])
+    assert len(plan) >= 6 and len({i for _, i in plan}) == 3
+    parity.compare_streams(cfg, o, res, min_open=3000)
+    st = [row[0] for row in res[0]["status"]]
+    assert max(s["ctcss_count"] + s["no_ctcss_count"] for s in st) > 0  # the NFM/CTCSS frequency did run

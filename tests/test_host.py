@@ -186,9 +186,6 @@ def test_missing_and_malformed_structure():
         host.parse_text('devices: ({ type = "rtlsdr"; sample_rate = 4000; centerfreq = 1.0; channels: ({ freq = 1.0; %s }); });' % OUT, 8000)
     with pytest.raises(host.ConfigError, match="invalid mode"):
         host.parse_text('devices: ({ type = "rtlsdr"; mode = "sweep"; centerfreq = 1.0; channels: ({ freq = 1.0; %s }); });' % OUT)
-    with pytest.raises(host.ConfigError, match="scan mode") as ei:
-        host.parse_text('devices: ({ type = "rtlsdr"; mode = "scan"; channels: ({ freqs = (1.0, 2.0); %s }); });' % OUT)
-    assert ei.value.code == host.ERR_UNSUPPORTED
     # a mixer output naming a defined mixer is fine
     ok = 'mixers: { m1: { %s } }; devices: ({ type = "rtlsdr"; centerfreq = 1.0; channels: ({ freq = 1.0; outputs: ({ type = "mixer"; name = "m1"; }); }); });' % OUT
     assert len(host.parse_text(ok).cfg.devices[0].channels) == 1
@@ -232,6 +229,93 @@ def test_mixers_connect_in_the_references_order():
     ]:
         with pytest.raises(host.ConfigError, match=msg):
             host.parse_text(bad)
+
+
+SCAN = """
+fft_size = 1024;
+devices: ({ type = "rtlsdr"; sample_rate = 2.4; mode = "scan";
+  channels: ({
+    freqs = ( 162.4, 162550000, "156.8M" );
+    labels = ( "a", "b", "c" );
+    modulations = ( "nfm", "am", "nfm" );
+    squelch_threshold = ( -40, 0, -55 );
+    squelch_snr_threshold = ( 6.0, -1, 3 );
+    notch = ( 100.0, 0.0, 250.0 ); notch_q = ( 0.0, 5.0, 4.0 );
+    ctcss = ( 0.0, 0.0, 88.5 );
+    bandwidth = ( 12500, 0, "8k" );
+    ampfactor = ( 1.0, 2.0, 0.5 );
+    afc = 3; tau = 300;
+    %(o)s }); });
+""" % {"o": OUT}
+
+
+def test_scan_mode_frequency_lists():
+    """R_SCAN (config.cpp:364-433): one channel, per-frequency lists, centre frequency 20 bins above the first frequency."""
+    c = host.parse_text(SCAN)
+    assert c.is_scan(0) and c.cfg.wave_rate == 16000
+    d = c.cfg.devices[0]
+    assert d.centerfreq == int(int(162.4 * 1e6) + 20 * float(2400000 // 1024))
+    ch = d.channels[0]
+    assert (ch.afc, ch.tau, len(ch.freqs)) == (3, 300, 3)
+    f = ch.freqs
+    assert [x.freq for x in f] == [int(162.4 * 1e6), 162550000, 156800000]
+    assert [x.modulation for x in f] == ["nfm", "am", "nfm"]
+    assert [x.squelch_threshold for x in f] == [-40, 0, -55]
+    assert [x.squelch_snr_threshold for x in f] == [6.0, -1.0, 3.0]  # -1 in a list keeps the default for that frequency
+    assert [(x.notch, x.notch_q) for x in f] == [(100.0, 10.0), (0.0, 0.0), (250.0, 4.0)]  # q 0 = default 10; notch 0 = off
+    assert [x.ctcss for x in f] == [0.0, 0.0, 88.5] and [x.bandwidth for x in f] == [12500, 0, 8000] and [x.ampfactor for x in f] == [1.0, 2.0, 0.5]
+    assert (ch.freq, ch.modulation, ch.bandwidth, ch.notch) == (f[0].freq, "nfm", 12500, 100.0)  # the channel's own fields repeat freqlist[0]
+    # scalars apply to every frequency
+    c2 = host.parse_text(SCAN.replace('modulations = ( "nfm", "am", "nfm" );', 'modulation = "nfm";').replace("ampfactor = ( 1.0, 2.0, 0.5 );", "ampfactor = 3.0;"))
+    assert [x.modulation for x in c2.cfg.devices[0].channels[0].freqs] == ["nfm"] * 3 and [x.ampfactor for x in c2.cfg.devices[0].channels[0].freqs] == [3.0] * 3
+    for bad, msg in [
+        (SCAN.replace("freqs = ( 162.4, 162550000, \"156.8M\" );", "freqs = ( );"), "freqs should be a list with at least one element"),
+        (SCAN.replace('labels = ( "a", "b", "c" );', 'labels = ( "a" );'), "labels should be a list with at least 3 elements"),
+        (SCAN.replace("squelch_threshold = ( -40, 0, -55 );", "squelch_threshold = ( -40 );"), "squelch_threshold should be an int or a list of ints with at least 3 elements"),
+        (SCAN.replace("ctcss = ( 0.0, 0.0, 88.5 );", "ctcss = ( 0.0 );"), "ctcss should be an float or a list of floats with at least 3 elements"),
+        (SCAN.replace('modulations = ( "nfm", "am", "nfm" );', 'modulations = ( "nfm", "am", "nfm" ); modulation = "am";'), "can't set both modulation and modulations"),
+        (SCAN.replace('modulations = ( "nfm", "am", "nfm" );', 'modulations = ( "nfm", "usb", "nfm" );'), r"modulations.\[1\]: unknown modulation"),
+        (SCAN.replace("notch_q = ( 0.0, 5.0, 4.0 );", "notch_q = ( 0.0, -5.0, 4.0 );"), r"freq.\[1\]: invalid value for notch_q"),
+        (SCAN.replace("%s }); });" % OUT, "%s }, { freqs = ( 1.0 ); %s }); });" % (OUT, OUT)), "only one channel is allowed in scan mode"),
+        (SCAN.replace("freqs = ", "freq = 1.0; nofreqs = "), r"mandatory parameter missing: devices.\[0\].channels.\[0\].freqs"),
+    ]:
+        with pytest.raises(host.ConfigError, match=msg):
+            host.parse_text(bad)
+
+
+def test_scan_controller_follows_the_references_thread():
+    """controller_thread (boondock_airband.cpp:101-139): polled every 200 ms; after 10 consecutive polls without signal it moves
+    to the next frequency at every further poll, a poll with signal resets the count (and tags the frequency once)."""
+    L = host.load_library()
+    st = (C.c_int32 * 4)(0, 0, -1, 3)  # i, consecutive_squelch_off, last_frequency, freq_count
+    L.ba_scan_controller_poll.argtypes = [C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int)]
+    seq, tags = [], []
+    polls = [0] * 13 + [1, 1] + [0] * 12 + [1]
+    for has_signal in polls:
+        tag = C.c_int(-1)
+        seq.append(L.ba_scan_controller_poll(st, has_signal, C.byref(tag)))
+        tags.append(tag.value)
+    # model of the loop
+    i = off = 0
+    last = -1
+    want, want_tags = [], []
+    for has_signal in polls:
+        tag = -1
+        if not has_signal:
+            if off < 10:
+                off += 1
+            else:
+                i = (i + 1) % 3
+        else:
+            if off == 10 and i != last:
+                tag = last = i
+            off = 0
+        want.append(i)
+        want_tags.append(tag)
+    assert seq == want and tags == want_tags
+    assert seq[9] == 0 and seq[10] == 1 and seq[12] == 0 and seq[13] == 0 and tags[13] == 0 and tags[14] == -1
+    one = (C.c_int32 * 4)(0, 0, -1, 1)  # freq_count < 2: the thread returns at once (:108-109)
+    assert [L.ba_scan_controller_poll(one, 0, None) for _ in range(15)] == [0] * 15
 
 
 def test_missing_type_falls_back_to_rtlsdr_with_the_warning():
@@ -318,17 +402,17 @@ def test_file_driver_checks():
 @pytest.mark.skipif(not os.path.isdir(REF_CONFIGS), reason="the reference tree is not mounted")
 def test_the_references_own_configuration_files():
     """Every multichannel example of the reference loads unchanged; derived bins follow config.cpp:669-670."""
-    seen = 0
+    seen = scans = 0
     for name in sorted(os.listdir(REF_CONFIGS)):
         path = os.path.join(REF_CONFIGS, name)
         text = open(path).read()
-        if 'mode = "scan"' in text:
-            with pytest.raises(host.ConfigError) as ei:
-                host.parse_file(path)
-            assert ei.value.code == host.ERR_UNSUPPORTED
-            continue
         c = host.parse_file(path)
-        n_entries = len(re.findall(r"^\s*freq\s*=", text, re.M))
+        for k, d in enumerate(c.cfg.devices):
+            if c.is_scan(k):
+                f0 = d.channels[0].freqs[0].freq
+                assert len(d.channels) == 1 and d.centerfreq == int(f0 + 20 * float(d.sample_rate // c.cfg.fft_size))  # config.cpp:431
+                scans += 1
+        n_entries = len(re.findall(r"^\s*freqs?\s*=", text, re.M))
         assert sum(len(d.channels) for d in c.cfg.devices) == n_entries, name
         assert sum(len(m.inputs) for m in c.cfg.mixers) == len(re.findall(r'type\s*=\s*"mixer"', text)), name
         for d in c.cfg.devices:
@@ -336,7 +420,9 @@ def test_the_references_own_configuration_files():
                 b = int(math.ceil((ch.freq + d.sample_rate - d.centerfreq) / float(d.sample_rate // c.cfg.fft_size) - 1.0)) % c.cfg.fft_size
                 assert 0 <= b < c.cfg.fft_size
         seen += 1
-    assert seen >= 4
+    assert seen >= 6 and scans >= 2
+    sc = host.parse_file(os.path.join(REF_CONFIGS, "basic_scanning.conf")).cfg.devices[0].channels[0]
+    assert [f.freq for f in sc.freqs] == [int(f * 1e6) for f in (118.15, 124.7, 132.1)]
     noaa = host.parse_file(os.path.join(REF_CONFIGS, "noaa.conf")).cfg
     assert noaa.wave_rate == 16000 and noaa.fft_size == 1024 and noaa.devices[0].sample_rate == int(2.40 * 1e6)
     assert all(ch.modulation == "nfm" and ch.bandwidth == 5000 and ch.squelch_snr_threshold == 0.0 and ch.ampfactor == 2.0 for ch in noaa.devices[0].channels)
