@@ -81,10 +81,55 @@ struct Geo {
     }
 };
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ float2 mul_mj(float2 a) { return make_float2(a.y, -a.x); } /* a * (-j) */
+/* Complex arithmetic on Blackwell's packed FP32 pairs: a float2 (re, im) lives in an aligned register pair and
+ * add/sub/mul/fma.rn.f32x2 (SASS FADD2/FMUL2/FFMA2) work on both halves at once.  ptxas folds component swaps, per-component
+ * sign flips and scalar broadcasts of the operands into the instruction (R.F32x2.LO_HI.NP, R.F32), so a complex add or
+ * subtract is ONE instruction, a multiply by -j is free, and a complex multiply is FMUL2 + FFMA2.  The kernel is bound by
+ * instruction issue (profiles/): this halves the FP32 instruction count of the butterflies, twiddles and the sample
+ * conversion.  Every component is still an individually rounded IEEE operation (the conversions stay bit-exact). */
+#ifdef BA_EMU
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#else
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+#endif
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return add2(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return sub2(a, b); }
+/* (a.x b.x - a.y b.y, a.y b.x + a.x b.y) = (-a.y, a.x) * b.y + a * b.x */
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return fma2(make_float2(-a.y, a.x), make_float2(b.y, b.y), mul2(a, make_float2(b.x, b.x))); }
+__device__ __forceinline__ float2 mul_mj(float2 a) { return make_float2(a.y, -a.x); } /* a * (-j): an operand swizzle of whatever reads it */
+/* a * exp(-j pi/4) = c * (a + a*(-j)) and a * exp(-3j pi/4) = c * (a*(-j) - a), c = sqrt(1/2) */
+__device__ __forceinline__ float2 rot_m45(float2 a, float c) { return mul2(add2(a, mul_mj(a)), make_float2(c, c)); }
+__device__ __forceinline__ float2 rot_m135(float2 a, float c) { return mul2(sub2(mul_mj(a), a), make_float2(c, c)); }
 
 template <int R>
 struct Dft;
@@ -121,9 +166,9 @@ struct Dft<8> {
             a[i] = cadd(x[i], x[i + 4]);
             b[i] = csub(x[i], x[i + 4]);
         }
-        b[1] = make_float2(c * (b[1].x + b[1].y), c * (b[1].y - b[1].x));
+        b[1] = rot_m45(b[1], c);
         b[2] = mul_mj(b[2]);
-        b[3] = make_float2(c * (b[3].y - b[3].x), -c * (b[3].x + b[3].y));
+        b[3] = rot_m135(b[3], c);
         Dft<4>::run(a);
         Dft<4>::run(b);
 #pragma unroll
@@ -145,11 +190,11 @@ struct Dft<16> {
         }
         /* b[i] *= exp(-2 pi i * i / 16) */
         b[1] = cmul(b[1], make_float2(c1, -s1));
-        b[2] = make_float2(c * (b[2].x + b[2].y), c * (b[2].y - b[2].x));
+        b[2] = rot_m45(b[2], c);
         b[3] = cmul(b[3], make_float2(s1, -c1));
         b[4] = mul_mj(b[4]);
         b[5] = cmul(b[5], make_float2(-s1, -c1));
-        b[6] = make_float2(c * (b[6].y - b[6].x), -c * (b[6].x + b[6].y));
+        b[6] = rot_m135(b[6], c);
         b[7] = cmul(b[7], make_float2(-c1, -s1));
         Dft<8>::run(a);
         Dft<8>::run(b);
@@ -190,20 +235,29 @@ __device__ __forceinline__ float level_s8(unsigned v) {
     return __fmul_rn((float)(int)(signed char)v, 0.0078125f);
 }
 
+/* both components of one u8 sample at once: the same four individually rounded operations as level_u8, then the window */
+__device__ __forceinline__ float2 sample_u8(unsigned v, float w) {
+    const float2 f = make_float2(__uint_as_float(__byte_perm(v, 0x47000000u, 0x7604u)), __uint_as_float(__byte_perm(v, 0x47000000u, 0x7614u)));
+    const float2 a = add2(f, make_float2(-32895.5f, -32895.5f)); /* v - 127.5, exact */
+    const float r_hi = 0x1.010102p-7f, r_lo = -0x1.fdfdfep-32f;
+    const float2 q = fma2(a, make_float2(r_hi, r_hi), mul2(a, make_float2(r_lo, r_lo)));
+    return mul2(q, make_float2(w, w));
+}
+
 template <int N, int FMT>
 __device__ __forceinline__ float2 load_sample(const unsigned char* frame, int n, float w, float scale) {
     if (FMT == BA_SFMT_U8) {
         const unsigned v = *reinterpret_cast<const unsigned short*>(frame + 2 * n);
-        return make_float2(__fmul_rn(level_u8<0>(v), w), __fmul_rn(level_u8<1>(v), w));
+        return sample_u8(v, w);
     } else if (FMT == BA_SFMT_S8) {
         const unsigned v = *reinterpret_cast<const unsigned short*>(frame + 2 * n);
         return make_float2(__fmul_rn(level_s8(v & 0xffu), w), __fmul_rn(level_s8(v >> 8), w));
     } else if (FMT == BA_SFMT_S16) {
         const short2 v = *reinterpret_cast<const short2*>(frame + 4 * n);
-        return make_float2(__fmul_rn(__fmul_rn(scale, (float)v.x), w), __fmul_rn(__fmul_rn(scale, (float)v.y), w));
+        return mul2(mul2(make_float2(scale, scale), make_float2((float)v.x, (float)v.y)), make_float2(w, w));
     } else {
         const float2 v = *reinterpret_cast<const float2*>(frame + 8 * n);
-        return make_float2(__fmul_rn(__fmul_rn(scale, v.x), w), __fmul_rn(__fmul_rn(scale, v.y), w));
+        return mul2(mul2(make_float2(scale, scale), v), make_float2(w, w));
     }
 }
 
