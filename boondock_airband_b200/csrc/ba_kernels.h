@@ -158,9 +158,6 @@ struct K2Params {
  * channel); s2/fork/join (optional) let the two kernels run concurrently */
 int k2_launch(const K2Params& p, int n_plain, cudaStream_t s, cudaStream_t s2, cudaEvent_t fork, cudaEvent_t join);
 
-/* the general demodulator held to 144 registers (14 warps per SM); demod.cu compiled with -DBA_K2_DENSE */
-int k2_dense_launch(const K2Params& p, int warps, cudaStream_t s);
-
 /* scan mode (boondock_airband.cpp:101-139,522): `chan`/`st` are the live entries of one channel, bank_* its per-frequency
  * copies.  Parks the freq_t part of the state (Squelch, filters, AGC level, active_counter) under `from`, loads the one
  * parked under `to` together with that frequency's constants; the channel_t part (look-back, phases, tails) stays. */
