@@ -11,8 +11,8 @@
  *   - the byte span of the tile (frames overlap by fft_size - hop samples) is brought into shared memory by ONE bulk
  *     copy (cp.async.bulk -> UBLKCP, completion on an mbarrier) into the idle half of a double buffer while the FFT groups
  *     work on the other half: every input byte is read from HBM/L2 once per tile and no thread waits on a global load;
- *   - an FFT is done by a group of G = N/16 threads (one warp for N = 512; a half warp for 256; 2..16 warps above),
- *     16 complex values per thread per pass, mixed radix 2/4/8/16 decimation in frequency, 2..4 passes;
+ *   - an FFT is done by a group of G = N/V threads, V = 16 complex values per thread per pass (32 for N = 512: a half warp
+ *     per FFT there and for 256; 2..16 warps above), mixed radix 2/4/8/16/32 decimation in frequency, 2..4 passes;
  *     window values and twiddles of a thread do not depend on the frame, they live in registers;
  *   - between passes the data goes through a per-group shared-memory buffer whose layouts are padded/skewed so that
  *     every 8-byte load and store of a half warp hits 16 distinct bank pairs;
@@ -29,27 +29,36 @@
 namespace ba {
 namespace {
 
+/* V complex values per thread, radices of the passes.  N = 512 keeps 32 values per thread (16 threads per FFT, two FFTs per
+ * warp) so that two passes (32 x 16) and ONE trip through shared memory do it: with the arithmetic on packed FP32 pairs the
+ * kernel is bound by the shared-memory pipe (profiles/), and the 8 x 8 x 8 plan made two trips. */
 template <int N>
 struct Plan;
-#define BA_PLAN(N_, P_, A, B, C, D)                                                         \
+#define BA_PLAN(N_, V_, T_, REGS_, P_, A, B, C, D)                                          \
     template <>                                                                             \
     struct Plan<N_> {                                                                       \
+        static constexpr int V = V_;       /* values per thread */                          \
+        static constexpr int THREADS = T_; /* threads per CTA */                            \
+        static constexpr int REGS = REGS_; /* register cap */                               \
         static constexpr int P = P_;                                                        \
         static constexpr int r(int i) { return i == 0 ? A : (i == 1 ? B : (i == 2 ? C : D)); } \
     };
-BA_PLAN(256, 2, 16, 16, 1, 1)
-BA_PLAN(512, 3, 8, 8, 8, 1)
-BA_PLAN(1024, 3, 4, 16, 16, 1)
-BA_PLAN(2048, 3, 8, 16, 16, 1)
-BA_PLAN(4096, 3, 16, 16, 16, 1)
-BA_PLAN(8192, 4, 2, 16, 16, 16)
+/* 112 registers: two CTAs of 256 threads leave 8192 registers per SM for the demodulator's warps, which run beside this kernel;
+ * the 32-value plan runs two CTAs of 128 threads under the same budget */
+BA_PLAN(256, 16, 256, 112, 2, 16, 16, 1, 1)
+BA_PLAN(512, 32, 128, 224, 2, 32, 16, 1, 1)
+BA_PLAN(1024, 16, 256, 112, 3, 4, 16, 16, 1)
+BA_PLAN(2048, 16, 256, 112, 3, 8, 16, 16, 1)
+BA_PLAN(4096, 16, 256, 112, 3, 16, 16, 16, 1)
+BA_PLAN(8192, 16, 512, 112, 4, 2, 16, 16, 16)
 
 template <int N>
 struct Geo {
     using PL = Plan<N>;
     static constexpr int P = PL::P;
-    static constexpr int G = N / 16; /* threads per FFT */
-    static constexpr int THREADS = (N >= 8192) ? 512 : 256;
+    static constexpr int V = PL::V;
+    static constexpr int G = N / V; /* threads per FFT */
+    static constexpr int THREADS = PL::THREADS;
     static constexpr int W = THREADS / G; /* FFT groups per CTA */
     static constexpr int WORK = N + N / 8; /* float2 per group */
     static constexpr int R(int pass) { return PL::r(pass - 1); } /* pass = 1..P */
@@ -206,6 +215,43 @@ struct Dft<16> {
     }
 };
 
+template <>
+struct Dft<32> {
+    static __device__ __forceinline__ void run(float2* x) {
+        /* exp(-2 pi i k / 32), k = 1..7 (cos, sin); the others follow by symmetry */
+        const float c1 = 0.98078528040323044913f, s1 = 0.19509032201612826785f, c2 = 0.92387953251128675613f, s2 = 0.38268343236508977173f;
+        const float c3 = 0.83146961230254523708f, s3 = 0.55557023301960222474f, c = 0.70710678118654752440f;
+        float2 a[16], b[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            a[i] = cadd(x[i], x[i + 16]);
+            b[i] = csub(x[i], x[i + 16]);
+        }
+        b[1] = cmul(b[1], make_float2(c1, -s1));
+        b[2] = cmul(b[2], make_float2(c2, -s2));
+        b[3] = cmul(b[3], make_float2(c3, -s3));
+        b[4] = rot_m45(b[4], c);
+        b[5] = cmul(b[5], make_float2(s3, -c3));
+        b[6] = cmul(b[6], make_float2(s2, -c2));
+        b[7] = cmul(b[7], make_float2(s1, -c1));
+        b[8] = mul_mj(b[8]);
+        b[9] = cmul(b[9], make_float2(-s1, -c1));
+        b[10] = cmul(b[10], make_float2(-s2, -c2));
+        b[11] = cmul(b[11], make_float2(-s3, -c3));
+        b[12] = rot_m135(b[12], c);
+        b[13] = cmul(b[13], make_float2(-c3, -s3));
+        b[14] = cmul(b[14], make_float2(-c2, -s2));
+        b[15] = cmul(b[15], make_float2(-c1, -s1));
+        Dft<16>::run(a);
+        Dft<16>::run(b);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            x[2 * i] = a[i];
+            x[2 * i + 1] = b[i];
+        }
+    }
+};
+
 template <int N>
 __device__ __forceinline__ void group_sync(int grp) {
     constexpr int G = Geo<N>::G;
@@ -264,8 +310,8 @@ __device__ __forceinline__ float2 load_sample(const unsigned char* frame, int n,
 /* per-thread constants that do not depend on the frame */
 template <int N>
 struct ThreadConst {
-    float win[16];
-    float2 tw[3][15];
+    float win[Geo<N>::V];
+    float2 tw[Geo<N>::P - 1][Geo<N>::V - 1];
 };
 
 template <int N, int PASS>
@@ -273,7 +319,7 @@ __device__ __forceinline__ void twiddle_setup(ThreadConst<N>& tc, const float2* 
     using GE = Geo<N>;
     if constexpr (PASS < GE::P) {
         constexpr int R = GE::R(PASS);
-        constexpr int NB = 16 / R;
+        constexpr int NB = GE::V / R;
         constexpr int Mp = GE::M(PASS);       /* positions per block after this pass */
         constexpr int Qprev = GE::Q(PASS - 1);
 #pragma unroll
@@ -293,7 +339,7 @@ __device__ __forceinline__ void fft_pass(const ThreadConst<N>& tc, float2* __res
                                          int grp, float2* dbg_in) {
     using GE = Geo<N>;
     constexpr int R = GE::R(PASS);
-    constexpr int NB = 16 / R;
+    constexpr int NB = GE::V / R;
     constexpr int Mp = GE::M(PASS);
     constexpr bool FIRST = PASS == 1, LAST = PASS == GE::P;
     float2 x[NB][R];
@@ -391,9 +437,8 @@ __device__ __forceinline__ void run_tile_frames(const ThreadConst<N>& tc, const 
 
 /* Persistent CTAs pull tiles from a launch-wide counter; the byte span of the next tile is fetched by one bulk copy
  * (cp.async.bulk, completion on an mbarrier) into the other half of a double buffer while the FFT groups work on this one. */
-/* 112 registers: two CTAs of 256 threads leave 8192 registers per SM for the demodulator's warps, which run beside this kernel */
 template <int N, bool DBG>
-__global__ void __maxnreg__(112) channelize_kernel(K1Params p) {
+__global__ void __maxnreg__(Plan<N>::REGS) channelize_kernel(K1Params p) {
     using GE = Geo<N>;
     BA_SHARED(smem);
     float2* work_all = reinterpret_cast<float2*>(smem + 2 * (size_t)p.raw_bytes);
@@ -410,7 +455,7 @@ __global__ void __maxnreg__(112) channelize_kernel(K1Params p) {
     ThreadConst<N> tc;
     {
         constexpr int R = GE::R(1);
-        constexpr int NB = 16 / R;
+        constexpr int NB = GE::V / R;
         constexpr int M1 = GE::M(1);
 #pragma unroll
         for (int i = 0; i < NB; i++) {
@@ -556,10 +601,11 @@ int k1_carry_launch(const K1Carry* list, int n, cudaStream_t s) {
 }
 
 int k1_threads(int n) {
-    return n >= 8192 ? 512 : 256;
+    return n >= 8192 ? Plan<8192>::THREADS : (n == 512 ? Plan<512>::THREADS : Plan<256>::THREADS);
 }
 int k1_groups(int n) {
-    return k1_threads(n) / (n / 16);
+    const int v = n == 512 ? Plan<512>::V : Plan<256>::V;
+    return k1_threads(n) / (n / v);
 }
 /* two halves of raw bytes, the FFT work buffers, the pick table, two mbarriers and the tile bookkeeping */
 int k1_smem_bytes(int n, int raw_bytes, int max_channels) {

@@ -262,3 +262,81 @@ def test_scan_mode(cuda, every):
     parity.compare_streams(cfg, o, res, min_open=3000)
     levels = {round(row[0]["squelch_level"], 6) for row in res[0]["status"]}
     assert len(levels) > 3  # the manual-level frequency and the automatic ones both ran
+
+
+def test_cfg5_full_size_replicas_and_oracle(cuda):
+    """BASELINE cfg 5 at its full size on one GPU: 512 inputs x 2.56 Msps u8, fft 512, 16 AM channels each (8192 channels, the
+    plain demodulator).  Size-independent properties: inputs that carry the same bytes under the same channel offsets
+    (every 8th input) give bit-identical audio and status, whichever SM and slot they ran on; one input of each of
+    the 8 kinds is compared with the oracle.  Inputs are device-resident, as in bench.py."""
+    torch = pytest.importorskip("torch")
+    from oracle.ba_oracle import Oracle
+    cfg = configs.cfg5(512, 512)
+    cfg.max_batches_per_step = 4
+    seconds = 1.3
+    tmpl = [synth.synth(cfg.devices[k], seconds, k, gate_on=0.35, gate_off=0.12) for k in range(8)]
+    dev_tmpl = [torch.from_numpy(t.copy()).cuda() for t in tmpl]
+    e = Engine(cfg, cuda)
+    keep = []
+    try:
+        for i in range(512):
+            t = dev_tmpl[i % 8].clone()  # a private copy per input, as separate dongles would have
+            keep.append(t)
+            e.attach_device_stream(i, t.data_ptr(), t.numel())
+        waves = [[] for _ in range(512)]
+        stats = [[] for _ in range(512)]
+        total = tmpl[0].size
+        for lo in range(0, total, 1_500_000):
+            n = min(1_500_000, total - lo)
+            for i in range(512):
+                e.advance_device_stream(i, n)
+            while True:
+                tk = e.process()
+                got = 0
+                for i in range(512):
+                    r = e.collect(tk, i)
+                    if r.n_batches:
+                        got += 1
+                        waves[i].append(r.waveout)
+                        stats[i].append(r.status_raw)
+                if not got:
+                    break
+        launches = e.launch_count()
+    finally:
+        e.close()
+    assert launches > 0
+    full = [np.concatenate(w, axis=1) for w in waves]
+    st = [np.concatenate(x, axis=0) for x in stats]
+    n_batches = full[0].shape[1] // cfg.wave_batch
+    assert n_batches == cfg.batches_for(0, total) and n_batches >= 9
+    for i in range(8, 512):
+        assert np.array_equal(full[i].view(np.uint32), full[i % 8].view(np.uint32)), "input %d differs from input %d" % (i, i % 8)
+        assert np.array_equal(st[i], st[i % 8]), "status of input %d differs from input %d" % (i, i % 8)
+    sub = abi.EngineCfg(fft_size=512, wave_rate=8000, devices=[cfg.devices[k] for k in range(8)])
+    o = Oracle(sub)
+    opened = 0
+    for k in range(8):
+        o.feed(k, tmpl[k])
+        for c in range(16):
+            wo = o.waveout(k, c)
+            assert len(wo) == full[k].shape[1]
+            assert float(np.abs(wo - full[k][c]).max()) <= parity.TOL_AUDIO
+            so = o.status(k, c)
+            for b, s_ in enumerate(so):
+                assert int(st[k][b, c, 0].view(np.int32)) == s_.axcindicate and int(st[k][b, c, 5]) == s_.open_count
+            opened += sum(1 for s_ in so if s_.axcindicate != abi.NO_SIGNAL)
+    assert opened > 100
+
+
+def test_cfg4_full_size(cuda):
+    """BASELINE cfg 4 at its full size: one 61.44 Msps cf32 stream, fft 8192, 2000 mixed AM/NFM channels (250 with CTCSS and
+    notch).  Squelch decisions identical, audio within 1e-3, for every channel."""
+    cfg = configs.cfg4()
+    cfg.flags = abi.FLAG_TRACE
+    cfg.max_batches_per_step = 2
+    torch = pytest.importorskip("torch")
+    n = int(0.3 * cfg.devices[0].sample_rate)  # 2000 carriers x 18 M samples: synthesised on the GPU, checked on the CPU
+    iq = synth.synth_torch(cfg.devices[0], n, 5, torch.device("cuda", 0), gate_on=0.12, gate_off=0.06).cpu().numpy()
+    torch.cuda.empty_cache()
+    o, res, _ = parity.run_both(cfg, [iq], cuda, chunk_bytes=64_000_000)
+    parity.compare_streams(cfg, o, res, min_open=100_000)
