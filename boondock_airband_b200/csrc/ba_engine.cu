@@ -432,9 +432,14 @@ int choose_tiles(ba_engine* e) {
     const int fixed = ba::k1_smem_bytes(N, 0, e->max_channels);
     /* budget: under half an SM's shared memory so that two CTAs are resident (registers allow it) with room left for the
      * demodulator's warps; the byte span of a tile is double-buffered */
-    const int budget = std::min(e->smem_optin, 96 * 1024);
+    /* experiment knobs (tuning runs only): resident channelizer CTAs per SM and frames per tile */
+    if (const char* v = getenv("BA_CUDA_K1_CTAS"))
+        e->k1_ctas_per_sm = std::max(1, atoi(v));
+    const int budget = std::min(e->smem_optin, (e->k1_ctas_per_sm > 2 ? 216 * 1024 / e->k1_ctas_per_sm : 96 * 1024));
     auto raw_of = [&](int tf) { return (((size_t)(tf - 1) * max_hop + max_frame + 32) + 15) & ~(size_t)15; };
     int tf = 4 * groups;
+    if (const char* v = getenv("BA_CUDA_K1_TILE"))
+        tf = std::max(groups, atoi(v) / groups * groups);
     while (tf > groups && (size_t)fixed + 2 * raw_of(tf) > (size_t)budget)
         tf -= groups;
     while (tf > 1 && (size_t)fixed + 2 * raw_of(tf) > (size_t)e->smem_optin)

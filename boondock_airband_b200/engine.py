@@ -40,7 +40,7 @@ class EngineError(RuntimeError):
 
 
 def load_library(path: Optional[str] = None):
-    path = path or LIB_PATH
+    path = path or os.environ.get("BA_CUDA_LIB") or LIB_PATH  # BA_CUDA_LIB: tuning runs with an alternative build
     if path in _LIBS:
         return _LIBS[path]
     if not os.path.exists(path):
