@@ -231,7 +231,8 @@ def main():
     step_bytes = 2 * FS * BATCHES_PER_STEP * (WAVE_RATE // 8) // WAVE_RATE  # bytes of one input per step (u8 IQ)
     # ---------------- device-resident run
     tmpl = make_templates(total_steps + 0.05, device)
-    cfg = workload_cfg(args.inputs, args.fft_size, rank * args.inputs, local)
+    from boondock_airband_b200 import sharding
+    cfg = workload_cfg(args.inputs, args.fft_size, sharding.first_input_of_rank(args.inputs, rank), local)
     eng = Engine(cfg)
     streams = []
     for i in range(args.inputs):
@@ -295,9 +296,7 @@ def main():
     assert batches == K * BATCHES_PER_STEP, "device-resident run produced %d batches, expected %d" % (batches, K * BATCHES_PER_STEP)
     elapsed = max(wall, dev_ms / 1e3)
     if world > 1:
-        tt = torch.tensor([elapsed], dtype=torch.float64, device=device)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        elapsed = float(tt.item())
+        elapsed = sharding.max_over_ranks(elapsed, dist, device)
     eng.close()
     del streams
     torch.cuda.empty_cache()
@@ -305,7 +304,7 @@ def main():
     # ---------------- end to end: pinned host IQ -> H2D -> kernels -> D2H audio, through the C-ABI
     e2e = None
     if not args.no_e2e:
-        cfg2 = workload_cfg(args.inputs, args.fft_size, rank * args.inputs, local)
+        cfg2 = workload_cfg(args.inputs, args.fft_size, sharding.first_input_of_rank(args.inputs, rank), local)
         eng2 = Engine(cfg2)
         host = []
         for i in range(TEMPLATES):
@@ -361,10 +360,8 @@ def main():
         windows.append((t0, t0 + e2e_wall))
         assert got == K * BATCHES_PER_STEP, "end-to-end run produced %d batches, expected %d" % (got, K * BATCHES_PER_STEP)
         if world > 1:
-            tt = torch.tensor([e2e_wall], dtype=torch.float64, device=device)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e_wall = float(tt.item())
-        e2e_msps = world * K * step_samples / e2e_wall / 1e6
+            e2e_wall = sharding.max_over_ranks(e2e_wall, dist, device)
+        e2e_msps = sharding.aggregate_msps(world, K, step_samples, e2e_wall)
         e2e = {"value": e2e_msps, "unit": "Msps", "x_realtime": e2e_msps * 1e6 / FS, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
                "ms_per_step": 1e3 * e2e_wall / K, "path": "ba_cuda_submit_external (pinned host) -> ba_cuda_process -> ba_cuda_collect",
                "legs_ms_per_step": {"h2d": e2e_legs[0] / K, "d2h": e2e_legs[1] / K, "channelize(K1)": e2e_legs[2] / K, "demod(K2)": e2e_legs[3] / K}}
@@ -401,7 +398,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    value = world * K * step_samples / elapsed / 1e6
+    value = sharding.aggregate_msps(world, K, step_samples, elapsed)
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
