@@ -31,7 +31,8 @@ namespace {
 
 /* V complex values per thread, radices of the passes.  N = 512 keeps 32 values per thread (16 threads per FFT, two FFTs per
  * warp) so that two passes (32 x 16) and ONE trip through shared memory do it: with the arithmetic on packed FP32 pairs the
- * kernel is bound by the shared-memory pipe (profiles/), and the 8 x 8 x 8 plan made two trips. */
+ * kernel is bound by the shared-memory pipe (profiles/), and the 8 x 8 x 8 plan made two trips.  N = 1024 likewise: 32 x 32,
+ * one warp per FFT. */
 template <int N>
 struct Plan;
 #define BA_PLAN(N_, V_, T_, REGS_, P_, A, B, C, D)                                          \
@@ -47,7 +48,7 @@ struct Plan;
  * the 32-value plan runs two CTAs of 128 threads under the same budget */
 BA_PLAN(256, 16, 256, 112, 2, 16, 16, 1, 1)
 BA_PLAN(512, 32, 128, 224, 2, 32, 16, 1, 1)
-BA_PLAN(1024, 16, 256, 112, 3, 4, 16, 16, 1)
+BA_PLAN(1024, 32, 128, 224, 2, 32, 32, 1, 1)
 BA_PLAN(2048, 16, 256, 112, 3, 8, 16, 16, 1)
 BA_PLAN(4096, 16, 256, 112, 3, 16, 16, 16, 1)
 BA_PLAN(8192, 16, 512, 112, 4, 2, 16, 16, 16)
@@ -600,12 +601,32 @@ int k1_carry_launch(const K1Carry* list, int n, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
+namespace {
+template <int N>
+void plan_of(int* threads, int* v) {
+    *threads = Plan<N>::THREADS;
+    *v = Plan<N>::V;
+}
+void plan_lookup(int n, int* threads, int* v) {
+    switch (n) {
+        case 256: plan_of<256>(threads, v); break;
+        case 512: plan_of<512>(threads, v); break;
+        case 1024: plan_of<1024>(threads, v); break;
+        case 2048: plan_of<2048>(threads, v); break;
+        case 4096: plan_of<4096>(threads, v); break;
+        default: plan_of<8192>(threads, v); break;
+    }
+}
+}  // namespace
 int k1_threads(int n) {
-    return n >= 8192 ? Plan<8192>::THREADS : (n == 512 ? Plan<512>::THREADS : Plan<256>::THREADS);
+    int t, v;
+    plan_lookup(n, &t, &v);
+    return t;
 }
 int k1_groups(int n) {
-    const int v = n == 512 ? Plan<512>::V : Plan<256>::V;
-    return k1_threads(n) / (n / v);
+    int t, v;
+    plan_lookup(n, &t, &v);
+    return t / (n / v);
 }
 /* two halves of raw bytes, the FFT work buffers, the pick table, two mbarriers and the tile bookkeeping */
 int k1_smem_bytes(int n, int raw_bytes, int max_channels) {
