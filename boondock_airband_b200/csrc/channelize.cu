@@ -32,7 +32,8 @@ namespace {
 /* V complex values per thread, radices of the passes.  N = 512 keeps 32 values per thread (16 threads per FFT, two FFTs per
  * warp) so that two passes (32 x 16) and ONE trip through shared memory do it: with the arithmetic on packed FP32 pairs the
  * kernel is bound by the shared-memory pipe (profiles/), and the 8 x 8 x 8 plan made two trips.  N = 1024 likewise: 32 x 32,
- * one warp per FFT. */
+ * one warp per FFT (cfg5 at fft 1024: 8.1 -> 6.5 ms per launch).  N = 8192: 32 x 16 x 16 with 256 threads, three passes
+ * instead of four (cfg4: 2.57 -> 2.35 ms).  2048 and 4096 need three passes either way and stay at 16 values. */
 template <int N>
 struct Plan;
 #define BA_PLAN(N_, V_, T_, REGS_, P_, A, B, C, D)                                          \
@@ -51,7 +52,7 @@ BA_PLAN(512, 32, 128, 224, 2, 32, 16, 1, 1)
 BA_PLAN(1024, 32, 128, 224, 2, 32, 32, 1, 1)
 BA_PLAN(2048, 16, 256, 112, 3, 8, 16, 16, 1)
 BA_PLAN(4096, 16, 256, 112, 3, 16, 16, 16, 1)
-BA_PLAN(8192, 16, 512, 112, 4, 2, 16, 16, 16)
+BA_PLAN(8192, 32, 256, 255, 3, 32, 16, 16, 1)
 
 template <int N>
 struct Geo {
