@@ -172,8 +172,53 @@ def make_templates(seconds_total: float, device):
     return [synth.synth_torch(cfg.devices[i], n, i, device) for i in range(TEMPLATES)]
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version when the box sets
+    NCCL_DEBUG): from here on file descriptor 1 is stderr, and emit() writes the result line to the real stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_RESULT_FD, data)
+
+
+def bind_near_gpu(local: int):
+    """Run this rank on the CPUs next to its GPU (NVML's affinity mask) BEFORE pinned host memory is allocated, so that
+    the rings and result buffers land on the GPU's NUMA node: with several ranks on one box the host<->device copies
+    otherwise cross sockets and share one memory controller.  Returns the mask to restore for the CPU-baseline leg."""
+    try:
+        before = os.sched_getaffinity(0)
+    except Exception:
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= before
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+    return before
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     rank, local, world = dist_env()
     if args.gpus != world and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE %d" % (args.gpus, world))
@@ -210,7 +255,7 @@ def main():
                 "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "Msps", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
                 "e2e": {"value": v, "unit": "Msps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     from boondock_airband_b200.engine import Engine
@@ -227,6 +272,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    affinity_before = bind_near_gpu(local)
     total_steps = K + W
     step_bytes = 2 * FS * BATCHES_PER_STEP * (WAVE_RATE // 8) // WAVE_RATE  # bytes of one input per step (u8 IQ)
     # ---------------- device-resident run
@@ -433,9 +479,11 @@ def main():
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu:
+        if affinity_before:
+            os.sched_setaffinity(0, affinity_before)  # the CPU baseline gets every host thread
         tmpl_host = [t[: 2 * 2 * FS].cpu().numpy() for t in tmpl]
         line["cpu_baseline"] = {k: v for k, v in cpu_reference(args.inputs, args.fft_size, args.cpu_seconds, tmpl_host).items() if k != "wall_s"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
