@@ -711,7 +711,7 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
         CU(cudaMemcpy(e->d_bank_state, bank_state.data(), sizeof(K2State) * bank_state.size(), cudaMemcpyHostToDevice));
     }
 
-    /* output arenas, two slots */
+    /* output arenas, one per slot */
     {
         size_t wave = 0, status = 0;
         for (Dev* d : e->dev) {
