@@ -276,6 +276,10 @@ def main():
     total_steps = K + W
     step_bytes = 2 * FS * BATCHES_PER_STEP * (WAVE_RATE // 8) // WAVE_RATE  # bytes of one input per step (u8 IQ)
     # ---------------- device-resident run
+    need = args.inputs * (total_steps + 0.05) * 2 * FS  # a private HBM copy of the whole timed stream per input
+    free_b, _total_b = torch.cuda.mem_get_info(local)
+    if need > 0.9 * free_b:
+        raise SystemExit("--steps %d --warmup %d needs %.0f GB of device-resident IQ (%.0f GB free): lower --steps" % (K, W, need / 1e9, free_b / 1e9))
     tmpl = make_templates(total_steps + 0.05, device)
     from boondock_airband_b200 import sharding
     cfg = workload_cfg(args.inputs, args.fft_size, sharding.first_input_of_rank(args.inputs, rank), local)
