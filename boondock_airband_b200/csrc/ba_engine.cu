@@ -437,7 +437,14 @@ int choose_tiles(ba_engine* e) {
         e->k1_ctas_per_sm = std::max(1, atoi(v));
     const int budget = std::min(e->smem_optin, (e->k1_ctas_per_sm > 2 ? 216 * 1024 / e->k1_ctas_per_sm : 96 * 1024));
     auto raw_of = [&](int tf) { return (((size_t)(tf - 1) * max_hop + max_frame + 32) + 15) & ~(size_t)15; };
+    /* four rounds of FFT groups per tile; six when a full step still leaves every resident CTA sixteen tiles or more
+     * (fewer tile hand-overs: 2 % on the 512-input workload), never so many that a small step no longer covers the SMs */
     int tf = 4 * groups;
+    {
+        const uint64_t frames_per_step = (uint64_t)e->dev.size() * e->max_batches * e->B;
+        if (frames_per_step / (6 * (uint64_t)groups) >= 16ull * e->sm_count * e->k1_ctas_per_sm)
+            tf = 6 * groups;
+    }
     if (const char* v = getenv("BA_CUDA_K1_TILE"))
         tf = std::max(groups, atoi(v) / groups * groups);
     while (tf > groups && (size_t)fixed + 2 * raw_of(tf) > (size_t)budget)

@@ -531,15 +531,21 @@ __global__ void __maxnreg__(Plan<N>::REGS) channelize_kernel(K1Params p) {
         const int fmt = dg->fmt;
         const int f0 = (tile - (int)dg->tile0) * p.tile_frames;
         const int nf = min(p.tile_frames, (int)c.n_frames - f0);
-        if (di != cur_dev) {
+        const bool new_dev = di != cur_dev; /* uniform over the CTA */
+        if (new_dev) {
             const uint32_t* bins = dg->bins;
             for (int ch = tid; ch < (int)c.n_channels; ch += GE::THREADS)
                 picktab[ch] = (uint16_t)GE::out_pos((int)(bins[ch] & (N - 1)));
             cur_dev = di;
         }
-        BA_MBAR_WAIT(&mbar[half], (parity >> half) & 1u);
+        BA_MBAR_WAIT(&mbar[half], (parity >> half) & 1u); /* every thread waits for the bytes itself */
         parity ^= 1u << half;
-        __syncthreads(); /* picktab is complete; (emulation: thread 0's copy has happened) */
+#ifdef BA_EMU
+        __syncthreads(); /* emulation: thread 0's copy has happened */
+#else
+        if (new_dev)
+            __syncthreads(); /* picktab is complete (consecutive tiles of a CTA mostly belong to one input: no barrier then) */
+#endif
 
         const unsigned char* raw0 = smem + (size_t)half * p.raw_bytes + s_pre[half];
         switch (fmt) {
