@@ -62,6 +62,11 @@ struct Geo {
     static constexpr int G = N / V; /* threads per FFT */
     static constexpr int THREADS = PL::THREADS;
     static constexpr int W = THREADS / G; /* FFT groups per CTA */
+    /* Two FFT groups share a warp when G = 16, and their frames lie a multiple of 128 bytes apart: read in the same order, the
+     * two half-warps would load their samples from the same banks.  The odd group therefore reads (and keeps) its samples
+     * rotated by one row of the first pass, x'[j] = x[(j + 1) mod R]; a rotation by r multiplies output k of that pass by
+     * W_R^(-rk), which the odd group's twiddles take back (they are per-thread constants anyway). */
+    static constexpr bool ROT = (G == 16) && (V / PL::r(0) == 1);
     static constexpr int WORK = N + N / 8; /* float2 per group */
     static constexpr int R(int pass) { return PL::r(pass - 1); } /* pass = 1..P */
     static constexpr int Q(int level) { /* blocks after `level` passes */
@@ -317,7 +322,7 @@ struct ThreadConst {
 };
 
 template <int N, int PASS>
-__device__ __forceinline__ void twiddle_setup(ThreadConst<N>& tc, const float2* __restrict__ table, int t) {
+__device__ __forceinline__ void twiddle_setup(ThreadConst<N>& tc, const float2* __restrict__ table, int t, int rot) {
     using GE = Geo<N>;
     if constexpr (PASS < GE::P) {
         constexpr int R = GE::R(PASS);
@@ -329,10 +334,14 @@ __device__ __forceinline__ void twiddle_setup(ThreadConst<N>& tc, const float2* 
             const int u = t + GE::G * i;
             const int m = u % Mp;
 #pragma unroll
-            for (int k = 1; k < R; k++)
-                tc.tw[PASS - 1][i * (R - 1) + (k - 1)] = table[k * m * Qprev];
+            for (int k = 1; k < R; k++) {
+                float2 w = table[k * m * Qprev];
+                if (PASS == 1 && GE::ROT && rot)
+                    w = cmul(w, table[(k * (N / R)) & (N - 1)]); /* W_R^k: undoes the rotation of the odd group's inputs */
+                tc.tw[PASS - 1][i * (R - 1) + (k - 1)] = w;
+            }
         }
-        twiddle_setup<N, PASS + 1>(tc, table, t);
+        twiddle_setup<N, PASS + 1>(tc, table, t, rot);
     }
 }
 
@@ -352,7 +361,11 @@ __device__ __forceinline__ void fft_pass(const ThreadConst<N>& tc, float2* __res
 #pragma unroll
         for (int j = 0; j < R; j++) {
             if (FIRST) {
-                const int n = j * Mp + m;
+                int n = j * Mp + m;
+                if (GE::ROT) { /* ((j + rot) mod R) * Mp + m */
+                    const int rot = grp & 1;
+                    n += rot * Mp - ((j == R - 1) ? rot * R * Mp : 0);
+                }
                 x[i][j] = load_sample<N, FMT>(frame, n, tc.win[i * R + j], scale);
                 if (dbg_in)
                     dbg_in[n] = x[i][j];
@@ -463,10 +476,14 @@ __global__ void __maxnreg__(Plan<N>::REGS) channelize_kernel(K1Params p) {
         for (int i = 0; i < NB; i++) {
             const int m = (t + GE::G * i) % M1;
 #pragma unroll
-            for (int j = 0; j < R; j++)
-                tc.win[i * R + j] = p.window[j * M1 + m];
+            for (int j = 0; j < R; j++) {
+                int n = j * M1 + m;
+                if (GE::ROT)
+                    n += (grp & 1) * M1 - ((j == R - 1) ? (grp & 1) * R * M1 : 0);
+                tc.win[i * R + j] = p.window[n];
+            }
         }
-        twiddle_setup<N, 1>(tc, p.twiddle, t);
+        twiddle_setup<N, 1>(tc, p.twiddle, t, GE::ROT ? (grp & 1) : 0);
     }
 
     /* thread 0: take the next tile off the counter and start the copy of its bytes into half `half` */
