@@ -451,6 +451,8 @@ int choose_tiles(ba_engine* e) {
         tf -= groups;
     while (tf > 1 && (size_t)fixed + 2 * raw_of(tf) > (size_t)e->smem_optin)
         tf--;
+    if (tf > 1)
+        tf &= ~1; /* tiles start on even frames of their launch (channelize.cu ties a rotation to the frame's parity) */
     const size_t raw = raw_of(tf);
     if ((size_t)fixed + 2 * raw > (size_t)e->smem_optin)
         return fail(BA_ERR_NOMEM, "K1 needs %zu bytes of shared memory per CTA, the device offers %d", (size_t)fixed + 2 * raw, e->smem_optin);

@@ -409,11 +409,16 @@ template <int N, int FMT, bool DBG>
 __device__ __forceinline__ void run_tile_frames(const ThreadConst<N>& tc, const TileCtx& c, const K1Device* dg, const unsigned char* raw0, float2* work,
                                                 const uint16_t* picktab, int f0, int nf, int t, int grp) {
     using GE = Geo<N>;
+    /* With rotated odd groups (Geo::ROT) a frame must meet the same rotation however the stream was cut into steps and tiles:
+     * the rotation follows the parity of the frame's index in the stream.  Tiles start on even frames of their launch, so
+     * swapping the two groups of a warp when the launch starts on an odd frame does it. */
+    const int swap = GE::ROT ? (int)(c.frame0 & 1ull) : 0;
     for (int base = 0; base < nf; base += GE::W) {
-        const bool live = base + grp < nf;
+        const int mine = base + (grp ^ swap);
+        const bool live = mine < nf;
         if (GE::G == 32 && !live)
             break; /* a group that is exactly one warp synchronises with nobody else */
-        const int fi = live ? base + grp : nf - 1; /* idle groups redo the last frame so that barriers stay uniform */
+        const int fi = live ? mine : nf - 1; /* idle groups redo the last frame so that barriers stay uniform */
         const unsigned char* frame = raw0 + (size_t)fi * c.hop_bytes;
         const int f = f0 + fi;
         float2* dbg_in = nullptr;
