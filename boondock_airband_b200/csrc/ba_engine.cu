@@ -160,6 +160,7 @@ struct ba_engine {
     int total_channels = 0, max_channels = 0;
     int stride = 0; /* max_batches*B + E */
     bool any_iq = false, any_afc = false;
+    bool serial_k2 = false; /* demodulator on the channelizer's stream (AFC needs it: the bins feed back) */
     cudaStream_t stream = nullptr; /* = s_k: kernels; debug helpers run here */
     cudaStream_t s_in = nullptr, s_k = nullptr, s_k2 = nullptr, s_out = nullptr; /* host->device, K1, K2, device->host */
     cudaStream_t s_k2b = nullptr; /* the plain-AM demodulator runs here beside the general one */
@@ -638,6 +639,7 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
     }
     if (e->any_afc)
         e->max_phases = e->max_batches + 1;
+    e->serial_k2 = e->any_afc;
 
     /* per-channel constants and state */
     const int TC = e->total_channels;
@@ -826,6 +828,19 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
     int rc = choose_tiles(e);
     if (rc != BA_OK)
         return rc;
+    /* The demodulator of ticket t may run beside the channelizer of ticket t+1 (two streams) or behind it (one stream).  A
+     * channelizer that fills every SM for milliseconds stretches the plain demodulator's serial chain beside it fourfold
+     * (measured: 0.87 ms alone, 1.1-4.2 ms beside K1), and the device->host copy of ticket t waits for that; with nothing but
+     * plain channels and a large step, one stream is faster (cfg5: 4.91 vs 5.07 ms per step at fft 512, 7.41 vs 7.71 at
+     * 1024).  Small steps and the long general demodulator keep the two streams (cfg3: 0.90 vs 0.96, cfg2 x 64: 8.56 vs 8.79). */
+    {
+        const uint64_t frames_per_step = (uint64_t)e->dev.size() * e->max_batches * e->B;
+        const bool big_step = frames_per_step / (uint64_t)std::max(1, e->tile_frames) >= 16ull * e->sm_count * e->k1_ctas_per_sm;
+        if (e->n_plain == e->total_channels && big_step)
+            e->serial_k2 = true;
+        if (const char* v = getenv("BA_CUDA_SERIAL_K2")) /* tuning runs only: 0 / 1 overrides the rule (AFC always serialises) */
+            e->serial_k2 = e->any_afc || atoi(v) != 0;
+    }
     CU(cudaStreamSynchronize(e->stream));
     guard.e = nullptr;
     *out = e;
@@ -984,7 +999,7 @@ int ba_cuda_process(ba_engine* e) {
         /* this slot last served ticket - BA_SLOTS: the descriptors its kernels read are rewritten below, its output arena is
          * rewritten by this ticket's demodulator (wait for its device->host copies) */
         CU(cudaStreamWaitEvent(e->s_in, s.ev_kdone, 0));
-        CU(cudaStreamWaitEvent(e->any_afc ? e->s_k : e->s_k2, s.ev_done, 0));
+        CU(cudaStreamWaitEvent(e->serial_k2 ? e->s_k : e->s_k2, s.ev_done, 0));
     }
     if (ticket >= 2) {
         /* ticket - 2: its channelizer read the input half-buffers that are refilled below, and its demodulator reads the
@@ -1247,7 +1262,7 @@ int ba_cuda_process(ba_engine* e) {
     /* 3. launches.  The channelizer (FP32/shared-memory bound, fills the SMs) and the demodulator (a latency-bound serial
      * recurrence, one or two warps per SM) run on two streams: the demodulator of ticket t overlaps the channelizer of
      * ticket t+1, which writes a disjoint stretch of the pick ring.  With AFC the bins feed back, so one stream is used. */
-    cudaStream_t k2s = e->any_afc ? e->s_k : e->s_k2;
+    cudaStream_t k2s = e->serial_k2 ? e->s_k : e->s_k2;
     for (int ph = 0; ph < phases; ph++) {
         CU(cudaEventRecord(s.ev_k[4 * ph + 0], e->s_k));
         if (k1_count[ph]) {
@@ -1464,7 +1479,7 @@ int ba_cuda_set_freq_idx(ba_engine* e, int dev, int channel, int freq_idx, uint6
     if (old == freq_idx)
         return BA_OK;
     /* behind every demodulator launch queued so far, ahead of the next one: park the freq_t state of `old`, bring in `freq_idx` */
-    cudaStream_t k2s = e->any_afc ? e->s_k : e->s_k2;
+    cudaStream_t k2s = e->serial_k2 ? e->s_k : e->s_k2;
     const size_t b0 = d->bank0[channel];
     const int gi = d->first_chan + channel;
     int rc = ba::k2_scan_switch_launch(e->d_chan + gi, e->d_state + gi, e->d_bank_chan + b0, e->d_bank_state + b0, old, freq_idx, k2s);
