@@ -228,7 +228,8 @@ def main():
                           "step = 1 s of signal per input (%d WAVE_BATCH batches)" % (args.inputs, args.fft_size, N_CHANNELS, WAVE_RATE, BATCHES_PER_STEP),
               "inputs_per_gpu": args.inputs, "sample_rate": FS, "sample_format": "u8", "fft_size": args.fft_size, "channels_per_input": N_CHANNELS,
               "wave_rate": WAVE_RATE, "samples_per_step_per_gpu": step_samples, "parallelism": "inputs sharded over GPUs, no collective",
-              "l2": "inputs larger than L2 (%.2f GB of fresh IQ per step)" % (2 * step_samples / 1e9)}
+              "l2": "inputs larger than L2 (%.2f GB of fresh IQ per step)" % (2 * step_samples / 1e9),
+              "results": "value: audio stays in HBM (BA_FLAG_RESULTS_ON_DEVICE), status returns to the host; value_results_to_host: audio copied to pinned host memory; e2e: host copies both ways"}
 
     import torch
 
@@ -282,30 +283,48 @@ def main():
         raise SystemExit("--steps %d --warmup %d needs %.0f GB of device-resident IQ (%.0f GB free): lower --steps" % (K, W, need / 1e9, free_b / 1e9))
     tmpl = make_templates(total_steps + 0.05, device)
     from boondock_airband_b200 import sharding
-    cfg = workload_cfg(args.inputs, args.fft_size, sharding.first_input_of_rank(args.inputs, rank), local)
-    eng = Engine(cfg)
     streams = []
     for i in range(args.inputs):
-        t = tmpl[i % TEMPLATES].clone()  # a private HBM copy per input
-        streams.append(t)
-        eng.attach_device_stream(i, t.data_ptr(), t.numel())
-    torch.cuda.synchronize()
-    # the first step also has to fill the AGC look-back (B + E frames): hand it a little more than one second
+        streams.append(tmpl[i % TEMPLATES].clone())  # a private HBM copy per input
     lead = 2 * FS // WAVE_RATE * 128 + 2 * args.fft_size
-    tickets = []
+    sampler = ClockSampler(local)
+    sampler.start()
+    windows = []
 
-    copy_legs = [0.0, 0.0]
+    def device_leg(flags):
+        """K timed steps with the IQ resident in HBM; flags: where the results go (see the two calls below)."""
+        from boondock_airband_b200 import abi
+        cfg = workload_cfg(args.inputs, args.fft_size, sharding.first_input_of_rank(args.inputs, rank), local)
+        cfg.flags = flags
+        eng = Engine(cfg)
+        for i, t in enumerate(streams):
+            eng.attach_device_stream(i, t.data_ptr(), t.numel())
+        torch.cuda.synchronize()
+        # the first step also has to fill the AGC look-back (B + E frames): hand it a little more than one second
+        tickets = []
 
-    def run_steps(n, first):
-        k1 = k2 = 0.0
-        batches = 0
-        for s in range(n):
-            extra = lead if (first and s == 0) else 0
-            for i in range(args.inputs):
-                eng.advance_device_stream(i, step_bytes + extra)
-            t = eng.process()
-            tickets.append(t)
-            if len(tickets) >= DEPTH:
+        copy_legs = [0.0, 0.0]
+
+        def run_steps(n, first):
+            k1 = k2 = 0.0
+            batches = 0
+            for s in range(n):
+                extra = lead if (first and s == 0) else 0
+                for i in range(args.inputs):
+                    eng.advance_device_stream(i, step_bytes + extra)
+                t = eng.process()
+                tickets.append(t)
+                if len(tickets) >= DEPTH:
+                    old = tickets.pop(0)
+                    r = eng.collect_raw(old, 0)
+                    a, b = eng.kernel_ms(old)
+                    k1 += a
+                    k2 += b
+                    h, d = eng.copy_ms(old)
+                    copy_legs[0] += h
+                    copy_legs[1] += d
+                    batches += r.n_batches
+            while tickets:
                 old = tickets.pop(0)
                 r = eng.collect_raw(old, 0)
                 a, b = eng.kernel_ms(old)
@@ -315,42 +334,40 @@ def main():
                 copy_legs[0] += h
                 copy_legs[1] += d
                 batches += r.n_batches
-        while tickets:
-            old = tickets.pop(0)
-            r = eng.collect_raw(old, 0)
-            a, b = eng.kernel_ms(old)
-            k1 += a
-            k2 += b
-            h, d = eng.copy_ms(old)
-            copy_legs[0] += h
-            copy_legs[1] += d
-            batches += r.n_batches
-        return k1, k2, batches
+            return k1, k2, batches
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    run_steps(W, True)
-    copy_legs[0] = copy_legs[1] = 0.0
-    launches0 = eng.launch_count()
-    barrier()
-    eng.mark(0)
-    t0 = time.perf_counter()
-    k1_ms, k2_ms, batches = run_steps(K, False)
-    eng.mark(1)
-    barrier()
-    t1 = time.perf_counter()
-    wall = t1 - t0
-    dev_ms = eng.mark_ms(0, 1)
-    windows = [(t0, t1)]
-    launches = eng.launch_count() - launches0
-    assert batches == K * BATCHES_PER_STEP, "device-resident run produced %d batches, expected %d" % (batches, K * BATCHES_PER_STEP)
-    # timed on the device (CUDA events on the engine's own streams, behind the barrier), max over ranks; the host's wall clock
-    # around the same region also contains the closing NCCL barrier and is reported next to it
-    elapsed = dev_ms / 1e3
-    if world > 1:
-        elapsed = sharding.max_over_ranks(elapsed, dist, device)
-        wall = sharding.max_over_ranks(wall, dist, device)
-    eng.close()
+        run_steps(W, True)
+        copy_legs[0] = copy_legs[1] = 0.0
+        launches0 = eng.launch_count()
+        barrier()
+        eng.mark(0)
+        t0 = time.perf_counter()
+        k1_ms, k2_ms, batches = run_steps(K, False)
+        eng.mark(1)
+        barrier()
+        t1 = time.perf_counter()
+        wall = t1 - t0
+        dev_ms = eng.mark_ms(0, 1)
+        windows.append((t0, t1))
+        launches = eng.launch_count() - launches0
+        assert batches == K * BATCHES_PER_STEP, "device-resident run produced %d batches, expected %d" % (batches, K * BATCHES_PER_STEP)
+        # timed on the device (CUDA events on the engine's own streams, behind the barrier), max over ranks; the host's wall clock
+        # around the same region also contains the closing NCCL barrier and is reported next to it
+        elapsed = dev_ms / 1e3
+        if world > 1:
+            elapsed = sharding.max_over_ranks(elapsed, dist, device)
+            wall = sharding.max_over_ranks(wall, dist, device)
+        eng.close()
+        return {"elapsed": elapsed, "wall": wall, "dev_ms": dev_ms, "k1_ms": k1_ms, "k2_ms": k2_ms, "launches": launches, "copy_legs": list(copy_legs)}
+
+    # `value`: IQ resident in HBM, results left in HBM for a consumer on the GPU (BA_FLAG_RESULTS_ON_DEVICE: ba_cuda_collect hands
+    # out device pointers; per-batch status still returns to the host) - no host copy in either direction inside the timed region.
+    # The same run with the audio returned to pinned host memory is reported beside it (`value_results_to_host`); the
+    # end-to-end leg below has host copies both ways.
+    from boondock_airband_b200 import abi as _abi
+    leg_dev = device_leg(_abi.FLAG_RESULTS_ON_DEVICE)
+    leg_host = device_leg(0)
+    elapsed, wall, dev_ms, k1_ms, k2_ms, launches, copy_legs = (leg_dev[k] for k in ("elapsed", "wall", "dev_ms", "k1_ms", "k2_ms", "launches", "copy_legs"))
     del streams
     torch.cuda.empty_cache()
 
@@ -482,7 +499,9 @@ def main():
                 "frac_of_spec_8000_gbs": achieved / 8000.0, "fma_pipe_busy_pct_ncu": fma_busy,
                 "note": "both kernels run concurrently on separate streams (K1 of pass t+1 beside K2 of pass t); per-kernel times are event-bracketed on their own streams"}
     line = {"metric": METRIC, "value": value, "unit": "Msps", "x_realtime": value * 1e6 / FS, "x_realtime_per_gpu": value * 1e6 / FS / world, "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": 1e3 * elapsed / K, "device_ms_per_step": dev_ms / K, "wall_ms_per_step": 1e3 * wall / K, "higher_is_better": True, "scaling": "weak",
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * elapsed / K, "device_ms_per_step": dev_ms / K, "wall_ms_per_step": 1e3 * wall / K,
+            "value_results_to_host": sharding.aggregate_msps(world, K, step_samples, leg_host["elapsed"]), "ms_per_step_results_to_host": 1e3 * leg_host["elapsed"] / K,
+            "results_d2h_ms_per_step_results_to_host": leg_host["copy_legs"][1] / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic (%d seeded streams, a private HBM copy per input)" % TEMPLATES, "config": config,
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline}
     if e2e is not None:

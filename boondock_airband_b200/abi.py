@@ -24,6 +24,7 @@ NO_SIGNAL, SIGNAL, AFC_UP, AFC_DOWN = ord(" "), ord("*"), ord("<"), ord(">")
 SQ_CLOSED, SQ_OPENING, SQ_CLOSING, SQ_LOW_SIGNAL_ABORT, SQ_OPEN = range(5)
 FLAG_TRACE = 0x1
 FLAG_KEEP_PICKS = 0x2
+FLAG_RESULTS_ON_DEVICE = 0x4
 TRACE_STATE_MASK, TRACE_OPEN, TRACE_AUDIO, TRACE_FILTERED = 0x07, 0x08, 0x10, 0x20
 
 OK = 0

@@ -836,7 +836,7 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
     {
         const uint64_t frames_per_step = (uint64_t)e->dev.size() * e->max_batches * e->B;
         const bool big_step = frames_per_step / (uint64_t)std::max(1, e->tile_frames) >= 16ull * e->sm_count * e->k1_ctas_per_sm;
-        if (e->n_plain == e->total_channels && big_step)
+        if (e->n_plain == e->total_channels && big_step && !(e->flags & BA_FLAG_RESULTS_ON_DEVICE)) /* with no copy waiting for K2, beside K1 is the shorter schedule */
             e->serial_k2 = true;
         if (const char* v = getenv("BA_CUDA_SERIAL_K2")) /* tuning runs only: 0 / 1 overrides the rule (AFC always serialises) */
             e->serial_k2 = e->any_afc || atoi(v) != 0;
@@ -1342,7 +1342,9 @@ int ba_cuda_process(ba_engine* e) {
             }
             return BA_OK;
         };
-        if (uniform && nb0 == e->max_batches && !s.d_trace) {
+        const bool to_host = !(e->flags & BA_FLAG_RESULTS_ON_DEVICE); /* else audio, iq_out and trace stay in HBM for a consumer on the GPU */
+        if (!to_host) {
+        } else if (uniform && nb0 == e->max_batches && !s.d_trace) {
             /* a full step everywhere: one linear copy of the arena (the E carried-over samples per row ride along, 1 %) */
             size_t floats = 0;
             for (Dev* d : e->dev)
@@ -1364,7 +1366,7 @@ int ba_cuda_process(ba_engine* e) {
                 }
         }
         for (Dev* d : e->dev) {
-            if (d->step_batches <= 0)
+            if (d->step_batches <= 0 || !to_host)
                 continue;
             if (s.d_iq && d->any_iq) {
                 const size_t width = (size_t)d->step_batches * B;
@@ -1385,9 +1387,10 @@ int ba_cuda_process(ba_engine* e) {
         }
     }
     if (mix_max_emit > 0) {
-        CU(cudaMemcpyAsync(s.h_mix, s.d_mix, sizeof(float) * e->mix_floats, cudaMemcpyDeviceToHost, e->s_out));
+        if (!(e->flags & BA_FLAG_RESULTS_ON_DEVICE))
+            CU(cudaMemcpyAsync(s.h_mix, s.d_mix, sizeof(float) * e->mix_floats, cudaMemcpyDeviceToHost, e->s_out));
         CU(cudaMemcpyAsync(s.h_mix_sig, s.d_mix_sig, sizeof(int32_t) * e->mixers.size() * e->max_batches, cudaMemcpyDeviceToHost, e->s_out));
-        s.d2h_bytes += sizeof(float) * e->mix_floats + sizeof(int32_t) * e->mixers.size() * e->max_batches;
+        s.d2h_bytes += ((e->flags & BA_FLAG_RESULTS_ON_DEVICE) ? 0 : sizeof(float) * e->mix_floats) + sizeof(int32_t) * e->mixers.size() * e->max_batches;
     }
     CU(cudaEventRecord(s.ev_done, e->s_out));
 
@@ -1430,9 +1433,10 @@ int ba_cuda_collect(ba_engine* e, int ticket, int dev, ba_step_out* out) {
     out->wave_batch = e->B;
     out->channel_count = d->C;
     out->wave_stride = e->stride;
-    out->waveout = s->h_wave + d->wave_off;
-    out->iq_out = (s->h_iq && d->any_iq) ? reinterpret_cast<const float*>(s->h_iq + d->iq_off) : nullptr;
-    out->trace = s->h_trace ? s->h_trace + d->wave_off : nullptr;
+    const bool on_dev = (e->flags & BA_FLAG_RESULTS_ON_DEVICE) != 0;
+    out->waveout = (on_dev ? s->d_wave : s->h_wave) + d->wave_off;
+    out->iq_out = (s->h_iq && d->any_iq) ? reinterpret_cast<const float*>((on_dev ? s->d_iq : s->h_iq) + d->iq_off) : nullptr;
+    out->trace = s->h_trace ? (on_dev ? s->d_trace : s->h_trace) + d->wave_off : nullptr;
     out->status = s->h_status + d->status_off;
     out->frames_done = s->frames_done[dev];
     return BA_OK;
@@ -1451,8 +1455,9 @@ int ba_cuda_collect_mixer(ba_engine* e, int ticket, int mixer, ba_mixer_out* out
     out->wave_batch = e->B;
     out->stereo = mx.stereo ? 1 : 0;
     out->first_batch = s->mix_first[mixer];
-    out->waveout = s->h_mix + mx.out_off;
-    out->waveout_r = mx.stereo ? s->h_mix + mx.out_off + (size_t)e->max_batches * e->B : nullptr;
+    const float* mix_base = (e->flags & BA_FLAG_RESULTS_ON_DEVICE) ? s->d_mix : s->h_mix;
+    out->waveout = mix_base + mx.out_off;
+    out->waveout_r = mx.stereo ? mix_base + mx.out_off + (size_t)e->max_batches * e->B : nullptr;
     out->axcindicate = s->h_mix_sig + (size_t)mixer * e->max_batches;
     return BA_OK;
 }

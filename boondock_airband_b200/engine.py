@@ -119,6 +119,29 @@ class StepResult:
                     no_ctcss_count=int(r[8]), active_counter=int(r[9]))
 
 
+_CUDART = None
+
+
+def device_to_host(ptr: int, nbytes: int) -> bytes:
+    """cudaMemcpy of a device range to host bytes (for callers that asked for BA_FLAG_RESULTS_ON_DEVICE and want to look)."""
+    global _CUDART
+    if _CUDART is None:
+        for name in ("libcudart.so", "libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so"):
+            try:
+                _CUDART = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        if _CUDART is None:
+            raise RuntimeError("libcudart not found")
+        _CUDART.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    buf = C.create_string_buffer(nbytes)
+    rc = _CUDART.cudaMemcpy(buf, C.c_void_p(ptr), nbytes, 2)  # cudaMemcpyDeviceToHost
+    if rc != 0:
+        raise RuntimeError("cudaMemcpy -> %d" % rc)
+    return buf.raw
+
+
 class Engine:
     def __init__(self, cfg: abi.EngineCfg, lib_path: Optional[str] = None):
         self.cfg = cfg

@@ -63,6 +63,10 @@ enum { BA_SQ_CLOSED = 0, BA_SQ_OPENING = 1, BA_SQ_CLOSING = 2, BA_SQ_LOW_SIGNAL_
 #define BA_FLAG_KEEP_PICKS 0x2u /* keep the picked-bin IQ of every channel on the device (ba_cuda_debug_picks); without it only
                                  * inputs with a channel that needs raw IQ (NFM, bandwidth, iq outputs) keep it, plain AM needs |X| only */
 
+#define BA_FLAG_RESULTS_ON_DEVICE 0x4u /* for consumers on the GPU (encoders, further DSP): waveout / iq_out / trace of ba_step_out
+                                        * and the planes of ba_mixer_out are DEVICE pointers into the ticket's result slot and are not
+                                        * copied to the host; status and axcindicate still are.  Valid until three more ba_cuda_process(). */
+
 /* trace byte layout: bits 0-2 Squelch current_state_, bit 3 is_open(), bit 4 should_process_audio(),
  * bit 5 should_filter_sample() && needs_raw_iq (the sample went through derotation/LPF) */
 #define BA_TRACE_STATE_MASK 0x07

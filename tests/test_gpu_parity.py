@@ -340,3 +340,33 @@ def test_cfg4_full_size(cuda):
     torch.cuda.empty_cache()
     o, res, _ = parity.run_both(cfg, [iq], cuda, chunk_bytes=64_000_000)
     parity.compare_streams(cfg, o, res, min_open=100_000)
+
+
+def test_results_on_device_equal_results_on_host(cuda):
+    """BA_FLAG_RESULTS_ON_DEVICE: the audio stays in HBM (device pointers in ba_step_out) - the same bytes a host copy gives."""
+    import ctypes as C
+    from boondock_airband_b200.engine import device_to_host
+    cfg, streams = scenarios.cfg1_short(0.6)
+    cfg.flags = 0
+    o, res, _ = parity.run_both(cfg, streams, cuda, chunk_bytes=500_000)
+    cfg.flags = abi.FLAG_RESULTS_ON_DEVICE
+    e = Engine(cfg, cuda)
+    waves = []
+    try:
+        iq = streams[0]
+        for lo in range(0, iq.size, 500_000):
+            e.submit(0, iq[lo:lo + 500_000])
+            t = e.process()
+            out = e.collect_raw(t, 0)
+            if out.n_batches:
+                n = out.n_batches * out.wave_batch
+                rows = []
+                for c in range(out.channel_count):
+                    ptr = C.cast(out.waveout, C.c_void_p).value + 4 * c * out.wave_stride
+                    rows.append(np.frombuffer(device_to_host(ptr, 4 * n), np.float32))
+                waves.append(np.stack(rows))
+                assert out.status[0].bin == e.channel_info(0, 0).bin  # status still arrives on the host
+    finally:
+        e.close()
+    got = np.concatenate(waves, axis=1)
+    assert np.array_equal(got.view(np.uint32), res[0]["waveout"].view(np.uint32))
