@@ -434,6 +434,7 @@ int choose_tiles(ba_engine* e) {
     /* budget: under half an SM's shared memory so that two CTAs are resident (registers allow it) with room left for the
      * demodulator's warps; the byte span of a tile is double-buffered */
     /* experiment knobs (tuning runs only): resident channelizer CTAs per SM and frames per tile */
+    e->k1_ctas_per_sm = ba::k1_ctas_per_sm(N);
     if (const char* v = getenv("BA_CUDA_K1_CTAS"))
         e->k1_ctas_per_sm = std::max(1, atoi(v));
     const int budget = std::min(e->smem_optin, (e->k1_ctas_per_sm > 2 ? 216 * 1024 / e->k1_ctas_per_sm : 96 * 1024));
