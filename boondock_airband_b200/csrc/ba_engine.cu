@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <deque>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -50,6 +51,16 @@ int fail(int code, const char* fmt, ...) {
             return fail(BA_ERR_CUDA, "%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+/* Every entry point that issues CUDA work first makes the engine's GPU the calling thread's current device: a process may
+ * hold one engine per GPU, each driven by its own demodulator thread (multiple_demod_threads, boondock_airband.cpp:1088-1122),
+ * and the current device is per-thread state that ba_cuda_create() set only on the thread that created the engine. */
+#define USE_DEVICE(e)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = cudaSetDevice((e)->cuda_device);                                               \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(BA_ERR_CUDA, "cudaSetDevice(%d) -> %s", (e)->cuda_device, cudaGetErrorString(e_)); \
+    } while (0)
+
 uint32_t pow2_at_least(uint64_t v) {
     uint32_t p = 1;
     while (p < v)
@@ -77,6 +88,8 @@ struct Dev {
     std::mutex lock;
     unsigned char* ring = nullptr;
     size_t buf_size = 0, mirror = 0, bufs = 0, bufe = 0;
+    size_t rpos = 0; /* the engine's read position: bytes in [bufs, rpos) have been queued for copying but the copy engine may still be
+                        reading them; bufs (what the producer sees, .cpp:735) follows once the copies have completed */
     uint64_t overflow_count = 0;
     std::vector<ExtChunk> ext;
     /* stream in HBM */
@@ -136,6 +149,8 @@ struct Slot {
     unsigned char* h_desc = nullptr;
     ba::K1Carry* h_carry = nullptr; /* pinned; the carry kernel reads it in place */
     cudaEvent_t ev_in2 = nullptr;   /* the second host->device stream has finished its share */
+    cudaEvent_t ev_ring = nullptr;  /* the copies out of the pinned input rings have completed */
+    std::vector<size_t> ring_taken; /* per device: ring bytes this ticket queued */
     cudaEvent_t ev_begin = nullptr, ev_done = nullptr; /* first operation of the ticket / results are in pinned host memory */
     cudaEvent_t ev_in = nullptr, ev_kdone = nullptr;    /* inputs and descriptors are in HBM / kernels have finished */
     cudaEvent_t ev_k1 = nullptr;                        /* the channelizer of the last phase has finished */
@@ -150,9 +165,17 @@ struct Slot {
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
 };
 
+/* ring bytes a ticket queued for copying: given back to the producers (bufs) once `ev` has fired */
+struct RingRelease {
+    cudaEvent_t ev;
+    std::vector<size_t> taken; /* per device */
+};
+
 }  // namespace
 
 struct ba_engine {
+    std::mutex rel_lock;
+    std::deque<RingRelease> rel;
     int fft_size = 0, wave_rate = 0, B = 0, fm_demod = 0, cuda_device = 0, max_batches = 0;
     uint32_t flags = 0;
     int sm_count = 0, smem_optin = 0;
@@ -207,6 +230,7 @@ namespace {
 void free_engine(ba_engine* e) {
     if (!e)
         return;
+    cudaSetDevice(e->cuda_device);
     for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2, e->s_k2b, e->s_out})
         if (q)
             cudaStreamSynchronize(q);
@@ -255,6 +279,8 @@ void free_engine(ba_engine* e) {
             cudaFreeHost(s.h_carry);
         if (s.ev_in2)
             cudaEventDestroy(s.ev_in2);
+        if (s.ev_ring)
+            cudaEventDestroy(s.ev_ring);
         if (s.ev_begin)
             cudaEventDestroy(s.ev_begin);
         if (s.ev_done)
@@ -816,6 +842,8 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
             CU(cudaEventCreate(&s.ev_kdone));
             CU(cudaEventCreate(&s.ev_out0));
             CU(cudaEventCreateWithFlags(&s.ev_in2, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s.ev_ring, cudaEventDisableTiming));
+            s.ring_taken.assign(nd, 0);
             if (cudaHostAlloc((void**)&s.h_carry, sizeof(ba::K1Carry) * std::max<size_t>(1, nd), cudaHostAllocDefault) != cudaSuccess)
                 return fail(BA_ERR_NOMEM, "pinned carry list");
             CU(cudaEventCreateWithFlags(&s.ev_k1, cudaEventDisableTiming));
@@ -829,6 +857,14 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
     int rc = choose_tiles(e);
     if (rc != BA_OK)
         return rc;
+    /* kernel attributes are per device: set them for this engine's GPU (the current device since cudaSetDevice above) */
+    {
+        int ke = k1_configure(N, e->raw_bytes, e->max_channels);
+        if (ke == 0)
+            ke = k2_configure();
+        if (ke != 0)
+            return fail(BA_ERR_CUDA, "kernel attributes on device %d: %s", e->cuda_device, cudaGetErrorString((cudaError_t)ke));
+    }
     /* The demodulator of ticket t may run beside the channelizer of ticket t+1 (two streams) or behind it (one stream).  A
      * channelizer that fills every SM for milliseconds stretches the plain demodulator's serial chain beside it fourfold
      * (measured: 0.87 ms alone, 1.1-4.2 ms beside K1), and the device->host copy of ticket t waits for that; with nothing but
@@ -869,9 +905,45 @@ int ba_cuda_input_ring(ba_engine* e, int dev, unsigned char** buffer, size_t* bu
     return BA_OK;
 }
 
-/* bytes waiting in the ring, as demodulate() computes them (.cpp:394-399) */
+/* bytes the producer may not overwrite yet, as demodulate() computes `available` (.cpp:394-399): from bufs to bufe */
 static size_t ring_available(const Dev& d) {
     return d.bufe >= d.bufs ? d.bufe - d.bufs : d.buf_size - d.bufs + d.bufe;
+}
+/* bytes the engine has not queued for copying yet: from its read position to bufe */
+static size_t ring_unread(const Dev& d) {
+    return d.bufe >= d.rpos ? d.bufe - d.rpos : d.buf_size - d.rpos + d.bufe;
+}
+
+/* bufs = (bufs + bps) % buf_size (.cpp:735), deferred: the copy engine reads the pinned ring asynchronously, so the bytes of a
+ * ticket go back to the producer only once the event behind its copies has fired.  Called (without blocking) from every entry
+ * point a producer or the demodulator thread passes through; `wait` blocks for the oldest pending ticket (a producer that
+ * found the ring full). */
+static void release_rings(ba_engine* e, bool wait) {
+    std::lock_guard<std::mutex> q(e->rel_lock); /* producers and the demodulator thread both come through here */
+    while (!e->rel.empty()) {
+        RingRelease& r = e->rel.front();
+        if (wait) {
+            if (cudaEventSynchronize(r.ev) != cudaSuccess)
+                return;
+            wait = false;
+        } else if (cudaEventQuery(r.ev) != cudaSuccess) {
+            return; /* copies complete in the order they were queued: nothing behind this one is done either */
+        }
+        for (size_t di = 0; di < e->dev.size(); di++)
+            if (r.taken[di]) {
+                Dev& d = *e->dev[di];
+                std::lock_guard<std::mutex> g(d.lock);
+                d.bufs = (d.bufs + r.taken[di]) % d.buf_size;
+            }
+        e->rel.pop_front();
+    }
+}
+static bool ring_release_pending(ba_engine* e, cudaEvent_t ev) {
+    std::lock_guard<std::mutex> q(e->rel_lock);
+    for (const RingRelease& r : e->rel)
+        if (r.ev == ev)
+            return true;
+    return false;
 }
 
 int ba_cuda_submit(ba_engine* e, int dev, const void* iq, size_t len) {
@@ -882,7 +954,10 @@ int ba_cuda_submit(ba_engine* e, int dev, const void* iq, size_t len) {
         return BA_OK;
     if (d->attached)
         return fail(BA_ERR_STATE, "input %d reads a device-resident stream", dev);
+    release_rings(e, false);
     std::lock_guard<std::mutex> g(d->lock);
+    if (!d->ext.empty())
+        return fail(BA_ERR_STATE, "input %d: external chunks pending; do not mix ring and external submissions within a step", dev);
     /* unlike circbuffer_append (which overwrites unread data and counts an overflow) the caller is told */
     if (len >= d->buf_size - ring_available(*d)) {
         d->overflow_count++;
@@ -907,6 +982,7 @@ int ba_cuda_input_space(ba_engine* e, int dev, size_t* free_bytes) {
     Dev* d = get_dev(e, dev);
     if (!d || !free_bytes)
         return fail(BA_ERR_BAD_ARG, "bad argument");
+    release_rings(e, false);
     std::lock_guard<std::mutex> g(d->lock);
     /* what ba_cuda_submit() accepts right now: one byte less than the unread gap (bufe may not catch up with bufs) */
     const size_t gap = d->buf_size - ring_available(*d);
@@ -920,7 +996,10 @@ int ba_cuda_commit(ba_engine* e, int dev, size_t len) {
         return BA_ERR_BAD_ARG;
     if (d->attached)
         return fail(BA_ERR_STATE, "input %d reads a device-resident stream", dev);
+    release_rings(e, false);
     std::lock_guard<std::mutex> g(d->lock);
+    if (!d->ext.empty())
+        return fail(BA_ERR_STATE, "input %d: external chunks pending; do not mix ring and external submissions within a step", dev);
     if (len >= d->buf_size - ring_available(*d)) {
         d->overflow_count++;
         return fail(BA_ERR_OVERRUN, "input %d: ring full", dev);
@@ -938,7 +1017,7 @@ int ba_cuda_submit_external(ba_engine* e, int dev, const void* iq, size_t len) {
     if (len == 0)
         return BA_OK;
     std::lock_guard<std::mutex> g(d->lock);
-    if (ring_available(*d))
+    if (ring_unread(*d))
         return fail(BA_ERR_STATE, "input %d: ring data pending; do not mix ring and external submissions within a step", dev);
     d->ext.push_back(ExtChunk{(const unsigned char*)iq, len});
     return BA_OK;
@@ -989,8 +1068,12 @@ int ba_cuda_process(ba_engine* e) {
     using namespace ba;
     if (!e)
         return fail(BA_ERR_BAD_ARG, "null engine");
+    USE_DEVICE(e);
     const int ticket = e->next_ticket;
     Slot& s = e->slot[ticket % BA_SLOTS];
+    release_rings(e, false);
+    while (ring_release_pending(e, s.ev_ring)) /* this slot's previous ticket (three steps back) still holds ring bytes: its copies finished long ago */
+        release_rings(e, true);
     if (s.busy) {
         /* the slot's previous ticket was never collected: its results are about to be replaced */
         CU(cudaEventSynchronize(s.ev_done));
@@ -1015,7 +1098,8 @@ int ba_cuda_process(ba_engine* e) {
     CU(cudaEventRecord(s.ev_begin, e->s_in));
 
     /* 1. move new bytes to HBM and decide how many frames and batches every input runs */
-    std::vector<size_t> ring_taken(nd, 0);
+    std::vector<size_t>& ring_taken = s.ring_taken;
+    std::fill(ring_taken.begin(), ring_taken.end(), (size_t)0);
     bool any_ring = false;
     /* host->device pieces are queued behind ALL the device->device carries of the step, so that the copy engine runs the
      * big transfers back to back instead of alternating directions per input */
@@ -1049,7 +1133,7 @@ int ba_cuda_process(ba_engine* e) {
                 const size_t cap_left = d.d_cap - carry;
                 if (want > cap_left)
                     want = cap_left;
-                take_ring = (size_t)std::min<uint64_t>(ring_available(d), want);
+                take_ring = (size_t)std::min<uint64_t>(ring_unread(d), want);
                 want -= take_ring;
                 while (want > 0 && !d.ext.empty()) {
                     ExtChunk& c = d.ext.front();
@@ -1068,13 +1152,14 @@ int ba_cuda_process(ba_engine* e) {
                     s.h_carry[n_carry++] = K1Carry{d.d_buf[nxt], d.d_buf[d.cur] + lo, (uint32_t)carry, 0u};
                 size_t at = carry;
                 if (take_ring) {
-                    const size_t first = std::min(take_ring, d.buf_size - d.bufs);
-                    pieces.push_back(Piece{d.d_buf[nxt] + at, d.ring + d.bufs, first});
+                    const size_t first = std::min(take_ring, d.buf_size - d.rpos);
+                    pieces.push_back(Piece{d.d_buf[nxt] + at, d.ring + d.rpos, first});
                     if (take_ring > first)
                         pieces.push_back(Piece{d.d_buf[nxt] + at + first, d.ring, take_ring - first});
                     at += take_ring;
                     s.h2d_bytes += take_ring;
                     ring_taken[di] = take_ring;
+                    d.rpos = (d.rpos + take_ring) % d.buf_size;
                     any_ring = true;
                 }
                 for (const ExtChunk& c : take_ext) {
@@ -1122,14 +1207,12 @@ int ba_cuda_process(ba_engine* e) {
         }
     }
     if (any_ring) {
-        /* the pinned rings are read by the copy engine: give the bytes back to the producers (bufs, .cpp:735) only once the copies are done */
-        CU(cudaStreamSynchronize(e->s_in));
-        for (size_t di = 0; di < nd; di++)
-            if (ring_taken[di]) {
-                Dev& d = *e->dev[di];
-                std::lock_guard<std::mutex> g(d.lock);
-                d.bufs = (d.bufs + ring_taken[di]) % d.buf_size;
-            }
+        /* the pinned rings are read by the copy engine: the bytes go back to the producers (bufs, .cpp:735) once this event has
+         * fired - checked without blocking by release_rings() at the next call of any entry point, so that this thread can go
+         * on planning and a producer thread can go on filling the ring while the copies and the kernels run */
+        CU(cudaEventRecord(s.ev_ring, e->s_in));
+        std::lock_guard<std::mutex> q(e->rel_lock);
+        e->rel.push_back(RingRelease{s.ev_ring, ring_taken});
     }
 
     /* 2. phases: one for ordinary inputs; an AFC input alternates K1/K2 per batch */
@@ -1427,7 +1510,9 @@ int ba_cuda_collect(ba_engine* e, int ticket, int dev, ba_step_out* out) {
     Dev* d = get_dev(e, dev);
     if (!s || !d || !out)
         return s && d ? fail(BA_ERR_BAD_ARG, "null out") : BA_ERR_BAD_ARG;
+    USE_DEVICE(e);
     CU(cudaEventSynchronize(s->ev_done));
+    release_rings(e, false);
     s->busy = false;
     memset(out, 0, sizeof(*out));
     out->n_batches = s->n_batches[dev];
@@ -1449,6 +1534,7 @@ int ba_cuda_collect_mixer(ba_engine* e, int ticket, int mixer, ba_mixer_out* out
         return BA_ERR_BAD_ARG;
     if (!out || mixer < 0 || mixer >= (int)e->mixers.size())
         return fail(BA_ERR_BAD_ARG, "no mixer %d", mixer);
+    USE_DEVICE(e);
     CU(cudaEventSynchronize(s->ev_done));
     const Mixer& mx = e->mixers[mixer];
     memset(out, 0, sizeof(*out));
@@ -1484,6 +1570,7 @@ int ba_cuda_set_freq_idx(ba_engine* e, int dev, int channel, int freq_idx, uint6
     const int old = d->freq_idx[channel];
     if (old == freq_idx)
         return BA_OK;
+    USE_DEVICE(e);
     /* behind every demodulator launch queued so far, ahead of the next one: park the freq_t state of `old`, bring in `freq_idx` */
     cudaStream_t k2s = e->serial_k2 ? e->s_k : e->s_k2;
     const size_t b0 = d->bank0[channel];
@@ -1500,6 +1587,7 @@ int ba_cuda_ticket_ms(ba_engine* e, int ticket, float* ms) {
     Slot* s = find_slot(e, ticket);
     if (!s || !ms)
         return BA_ERR_BAD_ARG;
+    USE_DEVICE(e);
     CU(cudaEventSynchronize(s->ev_done));
     CU(cudaEventElapsedTime(ms, s->ev_begin, s->ev_done));
     return BA_OK;
@@ -1509,6 +1597,7 @@ int ba_cuda_kernel_ms(ba_engine* e, int ticket, float ms[2]) {
     Slot* s = find_slot(e, ticket);
     if (!s || !ms)
         return BA_ERR_BAD_ARG;
+    USE_DEVICE(e);
     CU(cudaEventSynchronize(s->ev_done));
     ms[0] = ms[1] = 0.0f;
     for (int ph = 0; ph < s->phases; ph++) {
@@ -1525,6 +1614,7 @@ int ba_cuda_copy_ms(ba_engine* e, int ticket, float ms[2]) {
     Slot* s = find_slot(e, ticket);
     if (!s || !ms)
         return BA_ERR_BAD_ARG;
+    USE_DEVICE(e);
     CU(cudaEventSynchronize(s->ev_done));
     CU(cudaEventElapsedTime(&ms[0], s->ev_begin, s->ev_in));
     CU(cudaEventElapsedTime(&ms[1], s->ev_out0, s->ev_done));
@@ -1545,6 +1635,7 @@ int ba_cuda_step_bytes(ba_engine* e, int ticket, uint64_t* h2d, uint64_t* d2h) {
 int ba_cuda_mark(ba_engine* e, int which) {
     if (!e || which < 0 || which >= 8)
         return fail(BA_ERR_BAD_ARG, "bad mark %d", which);
+    USE_DEVICE(e);
     if (!e->marks[which])
         CU(cudaEventCreate(&e->marks[which]));
     for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2}) {
@@ -1558,6 +1649,7 @@ int ba_cuda_mark(ba_engine* e, int which) {
 int ba_cuda_mark_ms(ba_engine* e, int from, int to, float* ms) {
     if (!e || !ms || from < 0 || from >= 8 || to < 0 || to >= 8 || !e->marks[from] || !e->marks[to])
         return fail(BA_ERR_BAD_ARG, "marks %d, %d not recorded", from, to);
+    USE_DEVICE(e);
     CU(cudaEventSynchronize(e->marks[from]));
     CU(cudaEventSynchronize(e->marks[to]));
     CU(cudaEventElapsedTime(ms, e->marks[from], e->marks[to]));
@@ -1594,6 +1686,7 @@ int ba_cuda_debug_frames(ba_engine* e, int dev, const void* iq, size_t bytes, in
     const size_t N = (size_t)e->fft_size;
     if ((size_t)(n_frames - 1) * d->hop_bytes + d->frame_bytes > bytes)
         return fail(BA_ERR_BAD_ARG, "%d frames need %zu bytes, %zu given", n_frames, (size_t)(n_frames - 1) * d->hop_bytes + d->frame_bytes, bytes);
+    USE_DEVICE(e);
     unsigned char* d_iq = nullptr;
     float2 *d_in = nullptr, *d_out = nullptr, *d_picks = nullptr;
     float* d_mags = nullptr;
@@ -1678,6 +1771,7 @@ int ba_cuda_debug_picks(ba_engine* e, int dev, int channel, uint64_t first, int 
     if (first + (uint64_t)count > d->frames_done || d->frames_done - first > d->ring_len)
         return fail(BA_ERR_BAD_ARG, "frames [%llu, +%d) are not in the pick ring (frames done %llu, ring %u)", (unsigned long long)first, count,
                     (unsigned long long)d->frames_done, d->ring_len);
+    USE_DEVICE(e);
     CU(cudaStreamSynchronize(e->s_k));
     CU(cudaStreamSynchronize(e->s_k2));
     const float2* row = d->d_picks + (size_t)channel * d->ring_len;
@@ -1699,6 +1793,7 @@ int ba_cuda_debug_inject_picks(ba_engine* e, int dev, const float* picks, int n_
         return fail(BA_ERR_BAD_ARG, "bad argument");
     if ((uint64_t)n_frames > frame_room(e, *d))
         return fail(BA_ERR_OVERRUN, "input %d: room for %llu more frames before the next ba_cuda_process()", dev, (unsigned long long)frame_room(e, *d));
+    USE_DEVICE(e);
     CU(cudaStreamSynchronize(e->s_k));
     CU(cudaStreamSynchronize(e->s_k2));
     /* [frame][channel] from the caller -> the device's [channel][frame ring]; the magnitudes K1 would have written next to the

@@ -66,6 +66,8 @@ int k1_carry_launch(const K1Carry* list, int n, cudaStream_t s);
 
 /* returns 0 or a cudaError_t; dbg selects the instantiation that also serves dbg_in / dbg_out / spectrum */
 int k1_launch(int fft_size, const K1Params& p, int n_ctas, bool dbg, cudaStream_t s);
+/* sets the kernels' dynamic shared-memory limit on the CURRENT device; once per engine, after cudaSetDevice() */
+int k1_configure(int fft_size, int raw_bytes, int max_channels);
 int k1_smem_bytes(int fft_size, int raw_bytes, int max_channels);
 int k1_threads(int fft_size);
 int k1_groups(int fft_size); /* FFTs a CTA works on at a time */
@@ -158,6 +160,8 @@ struct K2Params {
 /* n_plain: the first n_plain slots of `order` are plain AM channels (demod_plain_kernel), the rest is general (one warp per
  * channel); s2/fork/join (optional) let the two kernels run concurrently */
 int k2_launch(const K2Params& p, int n_plain, cudaStream_t s, cudaStream_t s2, cudaEvent_t fork, cudaEvent_t join);
+/* sets the demodulators' dynamic shared-memory limit on the CURRENT device; once per engine, after cudaSetDevice() */
+int k2_configure(void);
 
 /* scan mode (boondock_airband.cpp:101-139,522): `chan`/`st` are the live entries of one channel, bank_* its per-frequency
  * copies.  Parks the freq_t part of the state (Squelch, filters, AGC level, active_counter) under `from`, loads the one

@@ -8,8 +8,11 @@
 #ifdef BA_EMU
 #include "cuda_emu.h"
 #define BA_SHARED(name) unsigned char* name = emu::tls().cta->smem
-#define BA_LAUNCH(kern, grid, block, smem, stream, ...) \
-    emu::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kern(__VA_ARGS__); })
+#define BA_LAUNCH(kern, grid, block, smem, stream, ...)                                  \
+    do {                                                                                  \
+        if (emu::launch_allowed((const void*)(kern), (size_t)(smem)))                     \
+            emu::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kern(__VA_ARGS__); }); \
+    } while (0)
 #define BA_BAR_SYNC(id, count) emu::bar_named((id), (count))
 /* cp.async: global -> shared without passing through registers; synchronous in the emulation */
 #define BA_CP_ASYNC_8(smem_ptr, gmem_ptr) memcpy((smem_ptr), (gmem_ptr), 8)
@@ -24,6 +27,10 @@
 #define BA_MBAR_EXPECT_TX(bar, bytes) ((void)(bar))
 #define BA_BULK_G2S(dst, src, bytes, bar) memcpy((dst), (src), (bytes))
 #define BA_MBAR_WAIT(bar, parity) ((void)(bar))
+/* flags in shared memory that one warp of a CTA publishes and another polls (the chunk FIFO between the demodulator's stages) */
+#define BA_FLAG_LOAD(p) __atomic_load_n((p), __ATOMIC_ACQUIRE)
+#define BA_FLAG_STORE(p, v) __atomic_store_n((p), (v), __ATOMIC_RELEASE)
+#define BA_SPIN_PAUSE() std::this_thread::yield()
 static inline unsigned atomicAdd(unsigned* p, unsigned v) {
     return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
@@ -39,6 +46,19 @@ static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
 #define BA_SHARED(name) extern __shared__ __align__(16) unsigned char name[]
 #define BA_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define BA_BAR_SYNC(id, count) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory")
+/* flags in shared memory that one warp of a CTA publishes and another polls (the chunk FIFO between the demodulator's stages):
+ * release/acquire at CTA scope orders the slot's contents with the counter */
+static __device__ __forceinline__ int ba_flag_load(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+static __device__ __forceinline__ void ba_flag_store(int* p, int v) {
+    asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+#define BA_FLAG_LOAD(p) ba_flag_load(p)
+#define BA_FLAG_STORE(p, v) ba_flag_store((p), (v))
+#define BA_SPIN_PAUSE() __nanosleep(40)
 #define BA_CP_ASYNC_8(smem_ptr, gmem_ptr) \
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_ptr)), "l"(gmem_ptr) : "memory")
 #define BA_CP_ASYNC_4(smem_ptr, gmem_ptr) \

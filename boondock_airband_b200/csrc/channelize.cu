@@ -595,16 +595,20 @@ template <int N, bool DBG>
 int launch_n(const K1Params& p, int n_ctas, cudaStream_t s) {
     using GE = Geo<N>;
     const size_t smem = (size_t)k1_smem_bytes(N, p.raw_bytes, p.max_channels);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(channelize_kernel<N, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess)
-            return (int)e;
-        configured = smem;
-    }
     auto kern = channelize_kernel<N, DBG>;
     BA_LAUNCH(kern, n_ctas, GE::THREADS, smem, s, p);
     return (int)cudaGetLastError();
+}
+
+/* The dynamic shared-memory limit of a kernel is an attribute of the (device, function) pair: the engine sets it once per
+ * engine, right after cudaSetDevice() in ba_cuda_create(), for both instantiations it may launch on that device - never
+ * through a process-wide flag (one process may drive one engine per GPU, boondock_airband.cpp:1088-1122). */
+template <int N>
+int configure_n(size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(channelize_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(channelize_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return (int)e;
 }
 
 template <int N>
@@ -669,6 +673,19 @@ int k1_groups(int n) {
 /* two halves of raw bytes, the FFT work buffers, the pick table, two mbarriers and the tile bookkeeping */
 int k1_smem_bytes(int n, int raw_bytes, int max_channels) {
     return 2 * raw_bytes + 8 * k1_groups(n) * (n + n / 8) + 2 * ((max_channels + 7) & ~7) + 64;
+}
+
+int k1_configure(int fft_size, int raw_bytes, int max_channels) {
+    const size_t smem = (size_t)k1_smem_bytes(fft_size, raw_bytes, max_channels);
+    switch (fft_size) {
+        case 256: return configure_n<256>(smem);
+        case 512: return configure_n<512>(smem);
+        case 1024: return configure_n<1024>(smem);
+        case 2048: return configure_n<2048>(smem);
+        case 4096: return configure_n<4096>(smem);
+        case 8192: return configure_n<8192>(smem);
+    }
+    return (int)cudaErrorInvalidValue;
 }
 
 int k1_launch(int fft_size, const K1Params& p, int n_ctas, bool dbg, cudaStream_t s) {

@@ -160,6 +160,10 @@ static inline void __syncwarp(unsigned = 0xffffffffu) {
     s.cta->warp[s.tid.x / 32]->arrive_and_wait();
 }
 
+static inline void __threadfence_block() {
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+}
+
 template <class T>
 static inline T __ldg(const T* p) {
     return *p;
@@ -271,15 +275,56 @@ enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaEventDefault = 0
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16, cudaDevAttrMaxSharedMemoryPerBlockOptin = 97 };
 
+/* Devices: BA_EMU_DEVICES (default 1) emulated GPUs; the current device is per-thread state as in the runtime, and the
+ * dynamic shared-memory limit of a kernel is kept per (device, kernel) as the driver keeps it: a launch that asks for more
+ * than 48 KB on a device where the attribute was never set fails with cudaErrorInvalidValue, exactly what happens to an
+ * engine on a second GPU when the attribute is cached per process. */
+namespace emu {
+inline int device_count() {
+    const char* v = getenv("BA_EMU_DEVICES");
+    const int n = v ? atoi(v) : 1;
+    return n > 0 ? n : 1;
+}
+inline int& current_device() {
+    static thread_local int d = 0;
+    return d;
+}
+inline int& last_error() {
+    static thread_local int e = 0;
+    return e;
+}
+struct FuncAttrs {
+    std::mutex lock;
+    std::vector<std::pair<std::pair<int, const void*>, size_t>> v;
+};
+inline FuncAttrs& func_attrs() {
+    static FuncAttrs f;
+    return f;
+}
+inline bool launch_allowed(const void* kern, size_t smem) {
+    if (smem <= 48 * 1024)
+        return true;
+    FuncAttrs& f = func_attrs();
+    std::lock_guard<std::mutex> g(f.lock);
+    for (auto& e : f.v)
+        if (e.first.first == current_device() && e.first.second == kern && e.second >= smem)
+            return true;
+    last_error() = 1; /* cudaErrorInvalidValue */
+    return false;
+}
+}  // namespace emu
 static inline cudaError_t cudaGetDeviceCount(int* n) {
-    *n = 1;
+    *n = emu::device_count();
     return cudaSuccess;
 }
-static inline cudaError_t cudaSetDevice(int) {
+static inline cudaError_t cudaSetDevice(int d) {
+    if (d < 0 || d >= emu::device_count())
+        return cudaErrorInvalidValue;
+    emu::current_device() = d;
     return cudaSuccess;
 }
 static inline cudaError_t cudaGetDevice(int* d) {
-    *d = 0;
+    *d = emu::current_device();
     return cudaSuccess;
 }
 static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {
@@ -367,7 +412,9 @@ static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEve
     return cudaSuccess;
 }
 static inline cudaError_t cudaGetLastError() {
-    return cudaSuccess;
+    const int e = emu::last_error();
+    emu::last_error() = 0;
+    return e;
 }
 static inline cudaError_t cudaPeekAtLastError() {
     return cudaSuccess;
@@ -376,7 +423,16 @@ static inline const char* cudaGetErrorString(cudaError_t e) {
     return e == cudaSuccess ? "no error" : "emulated CUDA error";
 }
 template <class K>
-static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) {
+static inline cudaError_t cudaFuncSetAttribute(K kern, cudaFuncAttribute, int bytes) {
+    emu::FuncAttrs& f = emu::func_attrs();
+    std::lock_guard<std::mutex> g(f.lock);
+    const std::pair<int, const void*> key(emu::current_device(), (const void*)kern);
+    for (auto& e : f.v)
+        if (e.first == key) {
+            e.second = (size_t)bytes;
+            return cudaSuccess;
+        }
+    f.v.push_back(std::make_pair(key, (size_t)bytes));
     return cudaSuccess;
 }
 
