@@ -56,6 +56,25 @@ def mixed_options(seconds=0.8, fmt="s16", fft_size=1024, fm_demod=abi.FM_FAST_AT
     return cfg, [iq]
 
 
+def afc_walk(seconds=1.6):
+    """AFC (boondock_airband.cpp:180-251) with carriers that do NOT sit in the channel's bin: the transmitters are placed by
+    one configuration, the receiver listens with another whose channels are tuned a few bins off.  Channel 0 is tuned two
+    bins below its carrier (the walk goes up: AFC_UP), channel 1 two bins above (AFC_DOWN), channel 2 one bin below with a
+    coarse afc step, channel 3 is on its carrier (no move), channel 4 is NFM through the low-pass, tuned one bin above.  The carriers gate on and off, so every open->closed edge
+    restores base_bins (.cpp:246-249) and every closed->open edge walks again."""
+    fs, cf, n = 2_560_000, 120_000_000, 512
+    bw = fs // n
+    tx_freqs = [cf - 800_000, cf - 400_000, cf + 100_000, cf + 500_000, cf + 900_000]
+    tx = DeviceCfg(sample_rate=fs, centerfreq=cf, sample_format="u8",
+                   channels=[ChannelCfg(freq=f) for f in tx_freqs[:4]] + [ChannelCfg(freq=tx_freqs[4], modulation="nfm")])
+    rx_ch = [ChannelCfg(freq=tx_freqs[0] - 2 * bw, afc=10), ChannelCfg(freq=tx_freqs[1] + 2 * bw, afc=10), ChannelCfg(freq=tx_freqs[2] - bw, afc=2),
+             ChannelCfg(freq=tx_freqs[3], afc=10), ChannelCfg(freq=tx_freqs[4] + bw, afc=10, modulation="nfm", bandwidth=12_500)]
+    rx = DeviceCfg(sample_rate=fs, centerfreq=cf, sample_format="u8", channels=rx_ch)
+    cfg = EngineCfg(fft_size=n, wave_rate=16000, devices=[rx], flags=abi.FLAG_TRACE, max_batches_per_step=3)
+    iq = synth.synth(tx, seconds, 77, gate_on=0.33, gate_off=0.2)
+    return cfg, [iq]
+
+
 def multi_device(seconds=0.5):
     """Three inputs of different sample formats and rates behind one engine (device_start..device_end of one demod thread)."""
     devs = []
