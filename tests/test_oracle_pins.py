@@ -340,3 +340,45 @@ def test_bin_and_phase_formulas(orc):
     assert info.bin == 989                   # Fs / N is an integer division: 2343, not 2343.75
     # dm_dphi: (freq - centre) / WAVE_RATE, fractional part, scaled to 24 bits; -82 kHz / 16 kHz = -5.125 -> -0.125 * 2^24
     assert info.dm_dphi == (int(-0.125 * (1 << 24)) & 0xFFFFFFFF)
+
+
+def _rn32(x):
+    """Round an exact rational to the nearest IEEE binary32 (ties to even); normal range only. Returns a Fraction."""
+    from fractions import Fraction
+    if x == 0:
+        return Fraction(0)
+    s = -1 if x < 0 else 1
+    a = abs(x)
+    e = 0
+    while a >= 2:
+        a /= 2
+        e += 1
+    while a < 1:
+        a *= 2
+        e -= 1
+    assert -126 <= e <= 127
+    m = a * (1 << 23)  # in [2^23, 2^24)
+    lo = m.numerator // m.denominator
+    rem = m - lo
+    if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and (lo & 1)):
+        lo += 1
+    return s * Fraction(lo, 1 << 23) * (Fraction(2) ** e)
+
+
+def test_u8_level_formula():
+    """K1 forms the u8 level (i - 127.5f) / 127.5f (boondock_airband.cpp:341-343) without a division:
+    fma(a, r_hi, RN(a * r_lo)) with a = i - 127.5 and a two-float reciprocal of 127.5 (channelize.cu: level_u8 / sample_u8).
+    Exact rational arithmetic: for all 256 codes the result equals the correctly rounded quotient, which is what the
+    reference's float division produces."""
+    from fractions import Fraction
+    r_hi = Fraction(float.fromhex("0x1.010102p-7"))
+    r_lo = Fraction(float.fromhex("-0x1.fdfdfep-32"))
+    assert _rn32(r_hi) == r_hi and _rn32(r_lo) == r_lo  # both are binary32 values
+    for code in range(256):
+        a = Fraction(2 * code - 255, 2)          # i - 127.5, exact in binary32
+        assert _rn32(a) == a
+        want = _rn32(a / Fraction(255, 2))       # IEEE division: the correctly rounded quotient
+        got = _rn32(a * r_hi + _rn32(a * r_lo))  # fma rounds once; the inner product is rounded separately
+        assert got == want, code
+        # and the table the reference fills is what numpy's float32 division gives
+        assert float(want) == float(np.float32(code - 127.5) / np.float32(127.5))
