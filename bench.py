@@ -7,10 +7,16 @@ every rank runs its own 512 inputs; inputs share no state, so there is no collec
 A "step" is one pass of the hot path (ba_cuda_process) over one second of signal of every input
 (8 WAVE_BATCH batches per channel): 512 x 2.56 M = 1310.72 M complex samples per GPU per step.
 
-  value      device-resident: every input's IQ already sits in HBM (its own buffer) when the timed region starts
+  value      every input's IQ already sits in HBM (its own buffer) when the timed region starts; the demodulated audio
+             returns to pinned host memory inside the timed region (BASELINE.json: "only demodulated audio returns to host");
+             value_results_on_device is the same run with the audio left in HBM for a consumer on the GPU
   e2e        the same steps through the C-ABI with HOST buffers: pinned host IQ -> H2D -> K1 -> K2 -> D2H of the audio
-  roofline   dominant kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json), algorithmic bytes
-             2*b*Fs + 4*C*R per input-second
+  roofline   dominant kernel (the channelizer) against the FP32 pipe (148 SMs x 128 lanes x 2 x 1.965 GHz, flops counted as
+             5 N log2 N + 4 N + 4 C per frame) and against the measured HBM copy bandwidth (MEASURED_PEAKS.json; algorithmic
+             bytes 2*b*Fs + 4*C*R per input-second)
+  workloads  (N = 1) the other BASELINE.json configurations, device-resident, audio to the host: cfg1, cfg2, one GPU's share of
+             cfg3, cfg4, cfg5 at fft 1024 / 2048 / 4096
+  strong     (N > 1) cfg5 as BASELINE.json defines it: 512 inputs IN TOTAL, split i mod G over the G GPUs
   cpu_baseline / --impl reference
              the reference's CPU path (oracle/_ref: the reference's own squelch/ctcss/filters objects driven by the
              restated demodulate() loop, Release flags) on the host cores, one thread per input as the reference does
@@ -53,6 +59,8 @@ def parse_args():
     ap.add_argument("--fft-size", type=int, default=FFT_SIZE)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true")
+    ap.add_argument("--total-inputs", type=int, default=512, help="inputs of the whole job in the strong-scaling leg (N > 1)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="signal seconds per input in the CPU sample")
     return ap.parse_args()
 
@@ -172,6 +180,30 @@ def make_templates(seconds_total: float, device):
     return [synth.synth_torch(cfg.devices[i], n, i, device) for i in range(TEMPLATES)]
 
 
+def other_workloads(device):
+    """The BASELINE.json configurations other than the headline one, measured inside this run (device-resident IQ, audio to
+    pinned host memory; tools/bench_workloads.py holds the harness): Msps, x real time, K1 / K2 milliseconds per step."""
+    import importlib.util
+
+    import torch
+    spec = importlib.util.spec_from_file_location("bench_workloads", os.path.join(ROOT, "tools", "bench_workloads.py"))
+    bw = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bw)
+    table = bw.workloads()
+    out = {}
+    for name in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5_n1024", "cfg5_n2048", "cfg5_n4096"):
+        text, make = table[name]
+        try:
+            r = bw.run(name, text, make, 4, 2, device)
+            out[name] = {"what": text, "msps": r["msps"], "x_realtime": r["x_realtime"], "x_realtime_aggregate": r["x_realtime_aggregate"], "ms_per_step": r["ms_per_step"],
+                         "channelize_ms_per_step": r["channelize_ms_per_step"], "demod_ms_per_step": r["demod_ms_per_step"], "inputs": r["inputs"], "channels": r["channels"],
+                         "fft_size": r["fft_size"], "steps": r["steps"], "warmup": r["warmup"]}
+        except Exception as ex:  # noqa: BLE001
+            out[name] = {"what": text, "error": repr(ex)}
+        torch.cuda.empty_cache()
+    return out
+
+
 _RESULT_FD = None
 
 
@@ -229,7 +261,7 @@ def main():
               "inputs_per_gpu": args.inputs, "sample_rate": FS, "sample_format": "u8", "fft_size": args.fft_size, "channels_per_input": N_CHANNELS,
               "wave_rate": WAVE_RATE, "samples_per_step_per_gpu": step_samples, "parallelism": "inputs sharded over GPUs, no collective",
               "l2": "inputs larger than L2 (%.2f GB of fresh IQ per step)" % (2 * step_samples / 1e9),
-              "results": "value: audio stays in HBM (BA_FLAG_RESULTS_ON_DEVICE), status returns to the host; value_results_to_host: audio copied to pinned host memory; e2e: host copies both ways"}
+              "results": "value: IQ resident in HBM, audio copied to pinned host memory; value_results_on_device: audio stays in HBM (BA_FLAG_RESULTS_ON_DEVICE), status returns to the host; e2e: host copies both ways"}
 
     import torch
 
@@ -291,13 +323,13 @@ def main():
     sampler.start()
     windows = []
 
-    def device_leg(flags):
-        """K timed steps with the IQ resident in HBM; flags: where the results go (see the two calls below)."""
-        from boondock_airband_b200 import abi
-        cfg = workload_cfg(args.inputs, args.fft_size, sharding.first_input_of_rank(args.inputs, rank), local)
+    def device_leg(flags, n_inputs=None, first_index=None):
+        """K timed steps with the IQ resident in HBM; flags: where the results go (see the calls below)."""
+        n_in = args.inputs if n_inputs is None else n_inputs
+        cfg = workload_cfg(n_in, args.fft_size, sharding.first_input_of_rank(args.inputs, rank) if first_index is None else first_index, local)
         cfg.flags = flags
         eng = Engine(cfg)
-        for i, t in enumerate(streams):
+        for i, t in enumerate(streams[:n_in]):
             eng.attach_device_stream(i, t.data_ptr(), t.numel())
         torch.cuda.synchronize()
         # the first step also has to fill the AGC look-back (B + E frames): hand it a little more than one second
@@ -310,7 +342,7 @@ def main():
             batches = 0
             for s in range(n):
                 extra = lead if (first and s == 0) else 0
-                for i in range(args.inputs):
+                for i in range(n_in):
                     eng.advance_device_stream(i, step_bytes + extra)
                 t = eng.process()
                 tickets.append(t)
@@ -360,14 +392,23 @@ def main():
         eng.close()
         return {"elapsed": elapsed, "wall": wall, "dev_ms": dev_ms, "k1_ms": k1_ms, "k2_ms": k2_ms, "launches": launches, "copy_legs": list(copy_legs)}
 
-    # `value`: IQ resident in HBM, results left in HBM for a consumer on the GPU (BA_FLAG_RESULTS_ON_DEVICE: ba_cuda_collect hands
-    # out device pointers; per-batch status still returns to the host) - no host copy in either direction inside the timed region.
-    # The same run with the audio returned to pinned host memory is reported beside it (`value_results_to_host`); the
-    # end-to-end leg below has host copies both ways.
+    # `value`: IQ resident in HBM, the demodulated audio copied to pinned host memory inside the timed region (the data flow
+    # BASELINE.json names).  The same run with the results left in HBM for a consumer on the GPU (BA_FLAG_RESULTS_ON_DEVICE:
+    # ba_cuda_collect hands out device pointers; per-batch status still returns to the host) is reported beside it as
+    # `value_results_on_device`; the end-to-end leg below has host copies both ways.
     from boondock_airband_b200 import abi as _abi
     leg_dev = device_leg(_abi.FLAG_RESULTS_ON_DEVICE)
     leg_host = device_leg(0)
-    elapsed, wall, dev_ms, k1_ms, k2_ms, launches, copy_legs = (leg_dev[k] for k in ("elapsed", "wall", "dev_ms", "k1_ms", "k2_ms", "launches", "copy_legs"))
+    elapsed, wall, dev_ms, k1_ms, k2_ms, launches, copy_legs = (leg_host[k] for k in ("elapsed", "wall", "dev_ms", "k1_ms", "k2_ms", "launches", "copy_legs"))
+    # strong scaling (N > 1): BASELINE.json's cfg5 is 512 inputs in total; input i of the job runs on GPU i mod G
+    strong = None
+    if world > 1:
+        mine = sharding.inputs_of_rank(args.total_inputs, world, rank)
+        leg_strong = device_leg(0, n_inputs=len(mine), first_index=mine[0] if mine else 0)
+        strong = {"total_inputs": args.total_inputs, "inputs_per_gpu": len(mine), "partition": "input i -> GPU i mod G", "ms_per_step": 1e3 * leg_strong["elapsed"] / K,
+                  "value": args.total_inputs * FS * K / leg_strong["elapsed"] / 1e6, "unit": "Msps", "results": "audio copied to pinned host memory",
+                  "kernels_ms_per_step": {"channelize(K1)": leg_strong["k1_ms"] / K, "demod(K2)": leg_strong["k2_ms"] / K}}
+        strong["x_realtime"] = strong["value"] * 1e6 / FS
     del streams
     torch.cuda.empty_cache()
 
@@ -478,11 +519,19 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     algo_bytes_step = args.inputs * (2 * 1 * FS + 4 * N_CHANNELS * WAVE_RATE)  # per GPU per step (1 s of signal per input)
+    # flops of the channelizer per frame, FFT convention: 5 N log2 N (butterflies) + 4 N (u8 conversion x window) + 4 C (magnitudes)
+    n_fft = args.fft_size
+    flops_frame = 5 * n_fft * (n_fft.bit_length() - 1) + 4 * n_fft + 4 * N_CHANNELS
+    algo_flops_step = args.inputs * BATCHES_PER_STEP * (WAVE_RATE // 8) * flops_frame
     kern = {"channelize(K1)": k1_ms / K, "demod(K2)": k2_ms / K}
     legs = {"descriptors_h2d_ms": copy_legs[0] / K, "results_d2h_ms": copy_legs[1] / K}
-    dom = max(kern, key=kern.get)
+    dom = "channelize(K1)"
     dom_ms = kern[dom]
-    achieved = algo_bytes_step / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+    sm_ghz = float(peaks.get("sm_max_mhz", 1965.0)) / 1e3
+    fp32_peak = sm_count * 128 * 2 * sm_ghz / 1e3  # TFLOP/s: 128 FP32 lanes per SM, one FMA = 2 flops
+    achieved_tf = algo_flops_step / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    achieved_gbs = algo_bytes_step / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernel, from the committed ncu --set full capture
     traffic, traffic_src, fma_busy = None, None, None
     try:
@@ -493,19 +542,33 @@ def main():
             fma_busy = tj.get("fma_pipe_busy_pct")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_src, "kernel_ms_per_launch": dom_ms, "algorithmic_bytes_per_launch": algo_bytes_step,
-                "all_kernels_ms_per_step": kern, "copy_legs_ms_per_step": legs,
-                "frac_of_spec_8000_gbs": achieved / 8000.0, "fma_pipe_busy_pct_ncu": fma_busy,
-                "note": "both kernels run concurrently on separate streams (K1 of pass t+1 beside K2 of pass t); per-kernel times are event-bracketed on their own streams"}
+    roofline = {"bound": "fp32", "kernel": dom, "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak,
+                "peak_source": "%d SMs x 128 FP32 lanes x 2 flops x %.3f GHz (no measured FP32 figure in MEASURED_PEAKS.json)" % (sm_count, sm_ghz),
+                "flop_convention": "per frame 5 N log2 N + 4 N + 4 C = %d (N = %d, C = %d); the kernel's own operation count is lower (radix 16/32 butterflies)" % (flops_frame, n_fft, N_CHANNELS),
+                "algorithmic_flops_per_launch": algo_flops_step, "frac_fp32": achieved_tf / fp32_peak,
+                "hbm": {"achieved": achieved_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved_gbs / peak, "frac_of_spec_8000_gbs": achieved_gbs / 8000.0,
+                        "algorithmic_bytes_per_launch": algo_bytes_step},
+                "frac_hbm": achieved_gbs / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel_ms_per_launch": dom_ms,
+                "all_kernels_ms_per_step": kern, "copy_legs_ms_per_step": legs, "fma_pipe_busy_pct_ncu": fma_busy,
+                "note": "kernel times are event-bracketed on the kernels' own streams in the `value` leg (audio to the host): there K2 of a step is queued behind "
+                        "K1 of the same step on one stream (plain-only large steps; ba_engine.cu), so K1 and K2 add up; in the results-on-device leg K2 of step t runs "
+                        "beside K1 of step t+1 on a second stream (its figures: value_results_on_device_kernels_ms_per_step)"}
+    value_dev = sharding.aggregate_msps(world, K, step_samples, leg_dev["elapsed"])
     line = {"metric": METRIC, "value": value, "unit": "Msps", "x_realtime": value * 1e6 / FS, "x_realtime_per_gpu": value * 1e6 / FS / world, "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": 1e3 * elapsed / K, "device_ms_per_step": dev_ms / K, "wall_ms_per_step": 1e3 * wall / K,
-            "value_results_to_host": sharding.aggregate_msps(world, K, step_samples, leg_host["elapsed"]), "ms_per_step_results_to_host": 1e3 * leg_host["elapsed"] / K,
-            "results_d2h_ms_per_step_results_to_host": leg_host["copy_legs"][1] / K, "higher_is_better": True, "scaling": "weak",
+            "results_d2h_ms_per_step": copy_legs[1] / K,
+            "value_results_on_device": value_dev, "ms_per_step_results_on_device": 1e3 * leg_dev["elapsed"] / K,
+            "value_results_on_device_kernels_ms_per_step": {"channelize(K1)": leg_dev["k1_ms"] / K, "demod(K2)": leg_dev["k2_ms"] / K},
+            "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic (%d seeded streams, a private HBM copy per input)" % TEMPLATES, "config": config,
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline}
+    if strong is not None:
+        line["strong"] = strong
     if e2e is not None:
         line["e2e"] = e2e
+    if world == 1 and not args.no_workloads:
+        line["workloads"] = other_workloads(device)
     if world == 1 and not args.no_cpu:
         if affinity_before:
             os.sched_setaffinity(0, affinity_before)  # the CPU baseline gets every host thread

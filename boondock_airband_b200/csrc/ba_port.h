@@ -58,7 +58,8 @@ static __device__ __forceinline__ void ba_flag_store(int* p, int v) {
 }
 #define BA_FLAG_LOAD(p) ba_flag_load(p)
 #define BA_FLAG_STORE(p, v) ba_flag_store((p), (v))
-#define BA_SPIN_PAUSE() __nanosleep(40)
+/* a chunk of the demodulator's pipelines takes well under a microsecond: no sleep between polls */
+#define BA_SPIN_PAUSE() ((void)0)
 #define BA_CP_ASYNC_8(smem_ptr, gmem_ptr) \
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_ptr)), "l"(gmem_ptr) : "memory")
 #define BA_CP_ASYNC_4(smem_ptr, gmem_ptr) \
