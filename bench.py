@@ -166,10 +166,39 @@ def cpu_reference(n_inputs_total: int, fft_size: int, seconds: float, templates_
     o.close()
     samples = n_inputs * (n_bytes // 2)
     msps = samples / wall / 1e6
-    return {"value": msps, "unit": "Msps", "x_realtime": msps * 1e6 / FS, "cores": min(threads, n_inputs), "host_threads": threads, "kind": kind,
-            "sample": "%d inputs x %.1f s of the same workload (cfg5: 2.56 Msps u8, fft %d, 16 AM channels), one thread per input, in-repo float FFT, "
-                      "-O3 -ffast-math -march=x86-64-v3, IQ fed from memory" % (n_inputs, seconds, fft_size),
-            "wall_s": wall}
+    lanes = o.fft_lanes()
+    fft_kind = ("in-repo AVX2+FMA radix-4 Stockham, eight consecutive frames per vector (oracle.cpp Fft8); the reference plans FFTW_MEASURE, FFTW is not installed on this box"
+                if lanes == 8 else "in-repo scalar radix-4 Stockham (no AVX2 on this host)")
+    out = {"value": msps, "unit": "Msps", "x_realtime": msps * 1e6 / FS, "cores": min(threads, n_inputs), "host_threads": threads, "kind": kind,
+           "sample": "%d inputs x %.1f s of the same workload (cfg5: 2.56 Msps u8, fft %d, 16 AM channels), one thread per input, IQ fed from memory" % (n_inputs, seconds, fft_size),
+           "fft_kind": fft_kind, "flags": "-O3 -ffast-math -march=x86-64-v3 (the binary travels to the GPU box), one translation unit instead of -flto",
+           "wall_s": wall}
+    try:
+        out.update(fft_witness(fft_size, min(threads, n_inputs), FS // WAVE_RATE))
+    except Exception as ex:  # noqa: BLE001
+        out["fft_only_witness_note"] = repr(ex)
+    return out
+
+
+def fft_witness(fft_size: int, threads: int, hop: int):
+    """What a tuned library FFT does on the same cores: torch.fft.fft (MKL / pocketfft) over a batch of complex64 frames, transform only -
+    no sample conversion, window, bin pick or demodulation - expressed as the input rate it would sustain (frames/s x hop).  The CPU
+    arm above does all of those; a reader can bound what FFTW would add or save from the two figures."""
+    import torch
+    before = torch.get_num_threads()
+    torch.set_num_threads(threads)
+    try:
+        x = torch.randn(threads * 2048, fft_size, dtype=torch.complex64)
+        torch.fft.fft(x, dim=1)
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            torch.fft.fft(x, dim=1)
+        dt = (time.perf_counter() - t0) / reps
+    finally:
+        torch.set_num_threads(before)
+    fps = x.shape[0] / dt
+    return {"fft_only_witness_msps": fps * hop / 1e6, "fft_only_witness": "torch.fft.fft, complex64, batch %d x %d, %d threads: %.2f us per frame per thread" % (x.shape[0], fft_size, threads, 1e6 * threads / fps)}
 
 
 def make_templates(seconds_total: float, device):

@@ -1008,6 +1008,16 @@ int ba_cuda_commit(ba_engine* e, int dev, size_t len) {
     return BA_OK;
 }
 
+int ba_cuda_input_consumed(ba_engine* e, int dev, size_t* bufs) {
+    Dev* d = get_dev(e, dev);
+    if (!d || !bufs)
+        return fail(BA_ERR_BAD_ARG, "bad argument");
+    release_rings(e, false);
+    std::lock_guard<std::mutex> g(d->lock);
+    *bufs = d->bufs;
+    return BA_OK;
+}
+
 int ba_cuda_submit_external(ba_engine* e, int dev, const void* iq, size_t len) {
     Dev* d = get_dev(e, dev);
     if (!d || (!iq && len))

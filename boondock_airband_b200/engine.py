@@ -26,7 +26,7 @@ _LIBS = {}
 # every symbol include/ba_cuda.h declares
 SYMBOLS = (
     "ba_cuda_create", "ba_cuda_destroy", "ba_cuda_last_error", "ba_cuda_visible_devices", "ba_cuda_input_ring",
-    "ba_cuda_submit", "ba_cuda_input_space", "ba_cuda_commit", "ba_cuda_submit_external", "ba_cuda_attach_device_stream",
+    "ba_cuda_submit", "ba_cuda_input_space", "ba_cuda_commit", "ba_cuda_input_consumed", "ba_cuda_submit_external", "ba_cuda_attach_device_stream",
     "ba_cuda_advance_device_stream", "ba_cuda_process", "ba_cuda_collect", "ba_cuda_collect_mixer", "ba_cuda_mixer_input_mask", "ba_cuda_set_freq_idx", "ba_cuda_ticket_ms", "ba_cuda_step_bytes",
     "ba_cuda_channel_info", "ba_cuda_window", "ba_cuda_debug_frames", "ba_cuda_debug_picks",
     "ba_cuda_debug_inject_picks", "ba_cuda_launch_count", "ba_cuda_kernel_ms", "ba_cuda_copy_ms", "ba_cuda_mark", "ba_cuda_mark_ms",

@@ -237,6 +237,9 @@ BA_API int ba_cuda_input_space(ba_engine* e, int dev, size_t* free_bytes);
 /* Same, for callers that wrote into the ring from ba_cuda_input_ring() themselves
  * (the rx thread of an unmodified input driver): publishes `bytes` more bytes at the ring's write index. */
 BA_API int ba_cuda_commit(ba_engine* e, int dev, size_t bytes);
+/* The ring's read index as demodulate() would have left it in input_t.bufs (bufs = (bufs + bps) % buf_size,
+ * src/boondock_airband.cpp:735): bytes before it have been copied to the device and may be overwritten by the rx thread. */
+BA_API int ba_cuda_input_consumed(ba_engine* e, int dev, size_t* bufs);
 
 /* Zero-copy variant for producers that already hold their samples in (ideally pinned) host memory: the bytes are
  * copied host->device straight from `iq` during the next ba_cuda_process() calls, without passing through the ring.

@@ -71,6 +71,8 @@ def load(ref: bool = False, fast: bool = False):
     L.ba_oracle_debug_frames.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, vp, vp]
     L.ba_oracle_run_threads.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_int]
     L.ba_oracle_run_threads.restype = C.c_double
+    L.ba_oracle_fft_lanes.argtypes = []
+    L.ba_oracle_fft_lanes.restype = C.c_int
     L.ba_oracle_sq_new.restype = vp
     L.ba_oracle_sq_free.argtypes = [vp]
     L.ba_oracle_sq_free.restype = None
@@ -183,6 +185,10 @@ class Oracle:
         if rc != 0:
             raise RuntimeError("ba_oracle_debug_frames: %s" % abi.ERRORS.get(rc, rc))
         return fi, fo
+
+    def fft_lanes(self) -> int:
+        """0: scalar transform (parity builds); 8: the AVX2 eight-frames-per-vector transform of the timing builds."""
+        return int(self.L.ba_oracle_fft_lanes())
 
     def run_threads(self, iqs, threads: int) -> float:
         """Timing leg: device i consumes iqs[i] entirely; one thread per device, `threads` at a time. Returns seconds."""

@@ -19,6 +19,14 @@
  *
  * Arithmetic: IEEE float, no contraction, no -ffast-math (the reference's own Release build uses -ffast-math
  * -march=native and is therefore not reproducible bit for bit across compilers).
+ *
+ * Timing builds (-DBA_ORACLE_FAST, the *_fast.so targets of oracle/Makefile; they serve bench.py's CPU legs only and are
+ * never compared bit for bit): the reference plans fftwf_plan_dft_1d(..., FFTW_MEASURE) and is built -O3 -ffast-math
+ * -march=native (boondock_airband.cpp:262-264, CMakeLists.txt:31-42), so a scalar transform would flatter the GPU.  FFTW is
+ * not installed here or on the GPU box; the timing builds therefore run an AVX2 + FMA transform written for this workload:
+ * eight consecutive frames at a time, one frame per vector lane (radix-4 Stockham, split real / imaginary arrays), with the
+ * sample conversion and window applied by 8 x 8 transposes on the way in.  bench.py reports it as fft_kind and puts a
+ * witness beside it (a batched torch.fft on the same cores).
  */
 #include <math.h>
 #include <stdint.h>
@@ -34,6 +42,11 @@
 #include <vector>
 
 #include "../include/ba_cuda.h"
+
+#if defined(BA_ORACLE_FAST) && defined(__AVX2__) && defined(__FMA__)
+#include <immintrin.h>
+#define BA_ORACLE_LANES 8
+#endif
 
 #ifdef BA_ORACLE_REF
 /* the FSM state is private in the reference and printed only under -DDEBUG_SQUELCH; the decision trace needs it */
@@ -134,6 +147,116 @@ struct Fft {
     }
 };
 
+
+#ifdef BA_ORACLE_LANES
+/* Timing builds only: the same radix-4 Stockham transform on eight frames at once, one frame per AVX2 lane.  Element k of
+ * the eight frames is one __m256 in re[] and one in im[]. */
+struct Fft8 {
+    int n = 0;
+    std::vector<float> tw;
+    std::vector<size_t> stage_off;
+    float* buf = nullptr; /* 4 arrays of n vectors: A.re A.im B.re B.im */
+    ~Fft8() { free(buf); }
+    Fft8() = default;
+    Fft8(const Fft8&) = delete;
+    Fft8& operator=(const Fft8&) = delete;
+    void plan(int size) {
+        n = size;
+        tw.clear();
+        stage_off.clear();
+        for (int len = n; len >= 4; len /= 4) {
+            stage_off.push_back(tw.size());
+            for (int p = 0; p < len / 4; p++)
+                for (int k = 1; k <= 3; k++) {
+                    double a = -2.0 * M_PI * (double)(p * k) / (double)len;
+                    tw.push_back((float)cos(a));
+                    tw.push_back((float)sin(a));
+                }
+        }
+        free(buf);
+        buf = (float*)aligned_alloc(64, sizeof(float) * 8 * (size_t)n * 4);
+    }
+    float* in_re() { return buf; }
+    float* in_im() { return buf + 8 * (size_t)n; }
+    /* transforms the frames in in_re()/in_im(); *out_re / *out_im point at the result arrays afterwards */
+    void run(const float** out_re, const float** out_im) {
+        float* a_re = buf;
+        float* a_im = buf + 8 * (size_t)n;
+        float* b_re = buf + 16 * (size_t)n;
+        float* b_im = buf + 24 * (size_t)n;
+        int s = 1, st = 0, len = n;
+        for (; len >= 4; len /= 4, s *= 4, st++) {
+            const int q1 = len / 4;
+            const float* w = tw.data() + stage_off[st];
+            for (int p = 0; p < q1; p++) {
+                const __m256 w1r = _mm256_set1_ps(w[6 * p + 0]), w1i = _mm256_set1_ps(w[6 * p + 1]);
+                const __m256 w2r = _mm256_set1_ps(w[6 * p + 2]), w2i = _mm256_set1_ps(w[6 * p + 3]);
+                const __m256 w3r = _mm256_set1_ps(w[6 * p + 4]), w3i = _mm256_set1_ps(w[6 * p + 5]);
+                const size_t ia = 8 * (size_t)s * p, ib = 8 * (size_t)s * (p + q1), ic = 8 * (size_t)s * (p + 2 * q1), id = 8 * (size_t)s * (p + 3 * q1);
+                const size_t o0 = 8 * (size_t)s * (4 * p);
+                for (int q = 0; q < s; q++) {
+                    const size_t e = 8 * (size_t)q;
+                    const __m256 ar = _mm256_load_ps(a_re + ia + e), ai = _mm256_load_ps(a_im + ia + e);
+                    const __m256 br = _mm256_load_ps(a_re + ib + e), bi = _mm256_load_ps(a_im + ib + e);
+                    const __m256 cr = _mm256_load_ps(a_re + ic + e), ci = _mm256_load_ps(a_im + ic + e);
+                    const __m256 dr = _mm256_load_ps(a_re + id + e), di = _mm256_load_ps(a_im + id + e);
+                    const __m256 apcr = _mm256_add_ps(ar, cr), apci = _mm256_add_ps(ai, ci), amcr = _mm256_sub_ps(ar, cr), amci = _mm256_sub_ps(ai, ci);
+                    const __m256 bpdr = _mm256_add_ps(br, dr), bpdi = _mm256_add_ps(bi, di);
+                    const __m256 jr = _mm256_sub_ps(di, bi), ji = _mm256_sub_ps(br, dr); /* j * (b - d) */
+                    _mm256_store_ps(b_re + o0 + e, _mm256_add_ps(apcr, bpdr));
+                    _mm256_store_ps(b_im + o0 + e, _mm256_add_ps(apci, bpdi));
+                    const __m256 t1r = _mm256_sub_ps(amcr, jr), t1i = _mm256_sub_ps(amci, ji);
+                    _mm256_store_ps(b_re + o0 + 8 * (size_t)s + e, _mm256_fmsub_ps(t1r, w1r, _mm256_mul_ps(t1i, w1i)));
+                    _mm256_store_ps(b_im + o0 + 8 * (size_t)s + e, _mm256_fmadd_ps(t1r, w1i, _mm256_mul_ps(t1i, w1r)));
+                    const __m256 t2r = _mm256_sub_ps(apcr, bpdr), t2i = _mm256_sub_ps(apci, bpdi);
+                    _mm256_store_ps(b_re + o0 + 16 * (size_t)s + e, _mm256_fmsub_ps(t2r, w2r, _mm256_mul_ps(t2i, w2i)));
+                    _mm256_store_ps(b_im + o0 + 16 * (size_t)s + e, _mm256_fmadd_ps(t2r, w2i, _mm256_mul_ps(t2i, w2r)));
+                    const __m256 t3r = _mm256_add_ps(amcr, jr), t3i = _mm256_add_ps(amci, ji);
+                    _mm256_store_ps(b_re + o0 + 24 * (size_t)s + e, _mm256_fmsub_ps(t3r, w3r, _mm256_mul_ps(t3i, w3i)));
+                    _mm256_store_ps(b_im + o0 + 24 * (size_t)s + e, _mm256_fmadd_ps(t3r, w3i, _mm256_mul_ps(t3i, w3r)));
+                }
+            }
+            std::swap(a_re, b_re);
+            std::swap(a_im, b_im);
+        }
+        if (len == 2) {
+            for (int q = 0; q < s; q++) {
+                const size_t e = 8 * (size_t)q, f = 8 * (size_t)(q + s);
+                const __m256 ar = _mm256_load_ps(a_re + e), ai = _mm256_load_ps(a_im + e), br = _mm256_load_ps(a_re + f), bi = _mm256_load_ps(a_im + f);
+                _mm256_store_ps(b_re + e, _mm256_add_ps(ar, br));
+                _mm256_store_ps(b_im + e, _mm256_add_ps(ai, bi));
+                _mm256_store_ps(b_re + f, _mm256_sub_ps(ar, br));
+                _mm256_store_ps(b_im + f, _mm256_sub_ps(ai, bi));
+            }
+            std::swap(a_re, b_re);
+            std::swap(a_im, b_im);
+        }
+        *out_re = a_re;
+        *out_im = a_im;
+    }
+};
+
+/* 8 x 8 transpose: rows r[0..7] (one frame each, eight consecutive samples) -> columns (one sample each, eight frames) */
+static inline void transpose8(__m256* r) {
+    const __m256 t0 = _mm256_unpacklo_ps(r[0], r[1]), t1 = _mm256_unpackhi_ps(r[0], r[1]);
+    const __m256 t2 = _mm256_unpacklo_ps(r[2], r[3]), t3 = _mm256_unpackhi_ps(r[2], r[3]);
+    const __m256 t4 = _mm256_unpacklo_ps(r[4], r[5]), t5 = _mm256_unpackhi_ps(r[4], r[5]);
+    const __m256 t6 = _mm256_unpacklo_ps(r[6], r[7]), t7 = _mm256_unpackhi_ps(r[6], r[7]);
+    const __m256 u0 = _mm256_shuffle_ps(t0, t2, 0x44), u1 = _mm256_shuffle_ps(t0, t2, 0xee);
+    const __m256 u2 = _mm256_shuffle_ps(t1, t3, 0x44), u3 = _mm256_shuffle_ps(t1, t3, 0xee);
+    const __m256 u4 = _mm256_shuffle_ps(t4, t6, 0x44), u5 = _mm256_shuffle_ps(t4, t6, 0xee);
+    const __m256 u6 = _mm256_shuffle_ps(t5, t7, 0x44), u7 = _mm256_shuffle_ps(t5, t7, 0xee);
+    r[0] = _mm256_permute2f128_ps(u0, u4, 0x20);
+    r[1] = _mm256_permute2f128_ps(u1, u5, 0x20);
+    r[2] = _mm256_permute2f128_ps(u2, u6, 0x20);
+    r[3] = _mm256_permute2f128_ps(u3, u7, 0x20);
+    r[4] = _mm256_permute2f128_ps(u0, u4, 0x31);
+    r[5] = _mm256_permute2f128_ps(u1, u5, 0x31);
+    r[6] = _mm256_permute2f128_ps(u2, u6, 0x31);
+    r[7] = _mm256_permute2f128_ps(u3, u7, 0x31);
+}
+#endif
+
 /* ---------------------------------------------------------------- helpers restated from the reference */
 
 /* util.cpp:103-127 — 256-entry sine/cosine table, argument formed in double and rounded to float, float sincosf */
@@ -221,6 +344,9 @@ struct Device {
     uint64_t frames = 0, batches = 0;
     std::vector<float> fftin, fftout;
     Fft fft;
+#ifdef BA_ORACLE_LANES
+    std::unique_ptr<Fft8> fft8;
+#endif
     float scale = 1.0f;
 };
 
@@ -467,11 +593,93 @@ inline void one_frame(ba_oracle* o, Device& d, const unsigned char* buf) {
         run_batch(o, d);
 }
 
+#ifdef BA_ORACLE_LANES
+/* Timing builds only: boondock_airband.cpp:426-516 for EIGHT consecutive frames starting at `buf` (frame f at buf + f * bps).
+ * The caller has made sure that no batch ends inside the group. */
+inline void eight_frames(ba_oracle* o, Device& d, const unsigned char* buf) {
+    const int N = o->fft_size;
+    Fft8& f8 = *d.fft8;
+    float* re = f8.in_re();
+    float* im = f8.in_im();
+    const float* window = o->window.data();
+    const __m256i unzip = _mm256_setr_epi32(0, 1, 4, 5, 2, 3, 6, 7);
+    const int fmt = d.cfg.sample_format;
+    const __m256 scale = _mm256_set1_ps(d.scale);
+    for (int n0 = 0; n0 < N; n0 += 8) {
+        __m256 r[8], q[8];
+        const __m256 w = _mm256_loadu_ps(window + n0);
+        for (int f = 0; f < 8; f++) {
+            __m256 lo, hi; /* I0 Q0 I1 Q1 I2 Q2 I3 Q3 and I4 Q4 .. Q7 of frame f, samples n0 .. n0 + 7 */
+            if (fmt == BA_SFMT_U8) {
+                const __m128i v = _mm_loadu_si128((const __m128i*)(buf + (size_t)f * d.bps + 2 * (size_t)n0));
+                const __m256 k = _mm256_set1_ps(1.0f / 127.5f), one = _mm256_set1_ps(1.0f);
+                lo = _mm256_fmsub_ps(_mm256_cvtepi32_ps(_mm256_cvtepu8_epi32(v)), k, one); /* (i - 127.5) / 127.5, .cpp:341-343 */
+                hi = _mm256_fmsub_ps(_mm256_cvtepi32_ps(_mm256_cvtepu8_epi32(_mm_srli_si128(v, 8))), k, one);
+            } else if (fmt == BA_SFMT_S8) {
+                const __m128i v = _mm_loadu_si128((const __m128i*)(buf + (size_t)f * d.bps + 2 * (size_t)n0));
+                const __m256 k = _mm256_set1_ps(1.0f / 128.0f);
+                lo = _mm256_mul_ps(_mm256_cvtepi32_ps(_mm256_cvtepi8_epi32(v)), k);
+                hi = _mm256_mul_ps(_mm256_cvtepi32_ps(_mm256_cvtepi8_epi32(_mm_srli_si128(v, 8))), k);
+            } else if (fmt == BA_SFMT_S16) {
+                const __m128i* b = (const __m128i*)(buf + (size_t)f * d.bps + 4 * (size_t)n0);
+                lo = _mm256_mul_ps(_mm256_cvtepi32_ps(_mm256_cvtepi16_epi32(_mm_loadu_si128(b))), scale);
+                hi = _mm256_mul_ps(_mm256_cvtepi32_ps(_mm256_cvtepi16_epi32(_mm_loadu_si128(b + 1))), scale);
+            } else {
+                const float* b = (const float*)(buf + (size_t)f * d.bps + 8 * (size_t)n0);
+                lo = _mm256_mul_ps(_mm256_loadu_ps(b), scale);
+                hi = _mm256_mul_ps(_mm256_loadu_ps(b + 8), scale);
+            }
+            /* de-interleave: even elements are I, odd are Q */
+            const __m256 ev = _mm256_permutevar8x32_ps(_mm256_shuffle_ps(lo, hi, 0x88), unzip);
+            const __m256 od = _mm256_permutevar8x32_ps(_mm256_shuffle_ps(lo, hi, 0xdd), unzip);
+            r[f] = _mm256_mul_ps(ev, w);
+            q[f] = _mm256_mul_ps(od, w);
+        }
+        transpose8(r);
+        transpose8(q);
+        for (int k = 0; k < 8; k++) {
+            _mm256_store_ps(re + 8 * (size_t)(n0 + k), r[k]);
+            _mm256_store_ps(im + 8 * (size_t)(n0 + k), q[k]);
+        }
+    }
+    const float *ore, *oim;
+    f8.run(&ore, &oim);
+    for (size_t j = 0; j < d.ch.size(); j++) {
+        Channel& c = d.ch[j];
+        const size_t bin = d.bins[j];
+        const __m256 xr = _mm256_load_ps(ore + 8 * bin), xi = _mm256_load_ps(oim + 8 * bin);
+        _mm256_storeu_ps(&c.wavein[d.waveend], _mm256_sqrt_ps(_mm256_fmadd_ps(xr, xr, _mm256_mul_ps(xi, xi))));
+        if (c.needs_raw_iq) {
+            alignas(32) float a[8], b[8];
+            _mm256_store_ps(a, xr);
+            _mm256_store_ps(b, xi);
+            for (int f = 0; f < 8; f++) {
+                c.iq_in[2 * (d.waveend + f)] = a[f];
+                c.iq_in[2 * (d.waveend + f) + 1] = b[f];
+            }
+        }
+    }
+    d.waveend += 8;
+    d.frames += 8;
+    if (d.waveend >= o->wave_batch + BA_AGC_EXTRA)
+        run_batch(o, d);
+}
+#endif
+
 /* consume as many frames as the reference's availability test allows (.cpp:418-424) from [p, p+len) */
 size_t consume(ba_oracle* o, Device& d, const unsigned char* p, size_t len) {
     const size_t need = d.bps + (size_t)o->fft_size * d.cfg.bytes_per_sample * 2;
     size_t off = 0;
     while (len - off >= need) {
+#ifdef BA_ORACLE_LANES
+        /* timing builds: eight frames at a time where nothing is recorded, no batch ends inside the group and AFC does not need
+         * the spectrum of a batch's last frame */
+        if (d.fft8 && !o->keep && len - off >= need + 7 * d.bps && d.waveend + 8 <= o->wave_batch + BA_AGC_EXTRA) {
+            eight_frames(o, d, p + off);
+            off += 8 * d.bps;
+            continue;
+        }
+#endif
         one_frame(o, d, p + off);
         off += d.bps;
     }
@@ -656,6 +864,17 @@ int ba_oracle_create(const ba_engine_desc* desc, int keep, ba_oracle** out) {
         d.ch.resize(d.cfg.channel_count);
         for (int ci = 0; ci < d.cfg.channel_count; ci++)
             fill_channel(o, d, d.ch[ci], d.cfg.channels[ci]);
+#ifdef BA_ORACLE_LANES
+        {
+            bool afc = false;
+            for (const Channel& c : d.ch)
+                afc = afc || c.afc != 0;
+            if (!afc && (N % 8) == 0) {
+                d.fft8.reset(new Fft8());
+                d.fft8->plan(N);
+            }
+        }
+#endif
         d.cfg.channels = nullptr;
     }
     *out = o;
@@ -786,6 +1005,15 @@ int ba_oracle_debug_frames(ba_oracle* o, int dev, const void* iq, size_t bytes, 
 
 /* Timing leg: every device consumes its whole buffer, one thread per device as the reference does with
  * multiple_demod_threads (boondock_airband.cpp:1088-1122), at most `threads` at a time.  Returns wall seconds. */
+/* which transform this build runs: 0 scalar radix-4 Stockham (parity builds), 8 the AVX2 eight-frames-per-vector one (timing builds) */
+int ba_oracle_fft_lanes(void) {
+#ifdef BA_ORACLE_LANES
+    return BA_ORACLE_LANES;
+#else
+    return 0;
+#endif
+}
+
 double ba_oracle_run_threads(ba_oracle* o, const void* const* iq, const size_t* bytes, int threads) {
     const int nd = (int)o->dev.size();
     if (threads < 1)
@@ -916,4 +1144,12 @@ extern "C" int ba_oracle_ctcss_run(float hz, float rate, int window, const float
         *enough = c.full;
     return c.has_tone();
 }
+#endif
+
+#if defined(BA_ORACLE_REF) && defined(BA_ORACLE_UNITY)
+/* timing build of the reference-objects oracle as ONE translation unit: the reference's own sources, compiled where they lie */
+#include "squelch.cpp"
+#include "ctcss.cpp"
+#include "filters.cpp"
+#include "logging.cpp"
 #endif

@@ -32,6 +32,8 @@ int ba_oracle_set_freq_idx(ba_oracle* o, int dev, int ch, uint64_t from_batch, i
 int ba_oracle_window(ba_oracle* o, float* out, size_t count);
 int ba_oracle_debug_frames(ba_oracle* o, int dev, const void* iq, size_t bytes, int n_frames, float* fftin, float* fftout);
 double ba_oracle_run_threads(ba_oracle* o, const void* const* iq, const size_t* bytes, int threads);
+/* 0: scalar transform (parity builds); 8: AVX2 transform, eight frames per vector (timing builds, -DBA_ORACLE_FAST) */
+int ba_oracle_fft_lanes(void);
 
 void* ba_oracle_sq_new(void);
 void ba_oracle_sq_free(void* s);
