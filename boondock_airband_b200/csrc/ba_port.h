@@ -50,11 +50,11 @@ static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
  * release/acquire at CTA scope orders the slot's contents with the counter */
 static __device__ __forceinline__ int ba_flag_load(const int* p) {
     int v;
-    asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
     return v;
 }
 static __device__ __forceinline__ void ba_flag_store(int* p, int v) {
-    asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+    asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 #define BA_FLAG_LOAD(p) ba_flag_load(p)
 #define BA_FLAG_STORE(p, v) ba_flag_store((p), (v))

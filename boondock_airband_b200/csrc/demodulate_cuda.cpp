@@ -14,8 +14,8 @@
  * What it needs from the reference beyond its headers:
  *   - `devices_running` (boondock_airband.cpp:74) without `static`, or this file appended to boondock_airband.cpp;
  *   - the raw configuration values of each channel, which parse_channels() reads and then folds into the Squelch / filter
- *     objects (config.cpp:437-622): ba_ref_channel_cfg(device, channel) returns them.  INTEGRATION.md section 3 has the
- *     patch to parse_channels() that records them (eight lines).
+ *     objects (config.cpp:437-622): ba_ref_channel_cfg(device, channel) returns them.  INTEGRATION.md section 3 shows where
+ *     they come from without touching config.cpp (libba_host.so's configuration front-end reads the same file).
  */
 #ifdef BA_WITH_REFERENCE_HEADERS
 #include "boondock_airband.h"
@@ -39,6 +39,9 @@ extern enum fm_demod_algo fm_demod;
  * squelch_threshold_dbfs, squelch_snr_threshold, notch, notch_q, ctcss, bandwidth, tau_us, and for scan mode the frequency
  * list.  frequency / modulation / ampfactor / afc / has_iq_outputs may be left zero: they are taken from channel_t. */
 extern "C" const ba_channel_desc* ba_ref_channel_cfg(int device, int channel);
+/* likewise the device's own settings; only tau_us is read (the device-level "tau", config.cpp:777-781: the reference keeps
+ * exp(-1 / (WAVE_RATE * tau)) in device_t::alpha, from which the integer cannot be recovered exactly).  May return NULL. */
+extern "C" const ba_device_desc* ba_ref_device_cfg(int device);
 /* output.cpp: disable_device_outputs(dev), called when an input has failed (boondock_airband.cpp:407-412) */
 void disable_device_outputs(device_t* dev);
 
@@ -60,7 +63,8 @@ void describe(int devno, device_t* dev, ba_device_desc* d, std::vector<ba_channe
     d->fullscale = in->fullscale;
     d->sample_rate = in->sample_rate;
     d->centerfreq = in->centerfreq;
-    d->tau_us = -1;
+    const ba_device_desc* rawdev = ba_ref_device_cfg(devno);
+    d->tau_us = rawdev ? rawdev->tau_us : -1;
     d->channel_count = dev->channel_count;
     for (int i = 0; i < dev->channel_count; i++) {
         channel_t* c = dev->channels + i;

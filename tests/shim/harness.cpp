@@ -36,6 +36,7 @@ void disable_device_outputs(device_t*) {}
 
 namespace {
 std::vector<std::vector<ba_channel_desc> > g_cfg;
+std::vector<ba_device_desc> g_devcfg;
 struct Feed {
     input_t* in;
     const unsigned char* data;
@@ -127,6 +128,12 @@ extern "C" const ba_channel_desc* ba_ref_channel_cfg(int device, int channel) {
     return &g_cfg[device][channel];
 }
 
+extern "C" const ba_device_desc* ba_ref_device_cfg(int device) {
+    if (device < 0 || device >= (int)g_devcfg.size())
+        return NULL;
+    return &g_devcfg[device];
+}
+
 extern "C" {
 __attribute__((visibility("default"))) int ba_shim_wave_rate(void) { return WAVE_RATE; }
 
@@ -148,6 +155,7 @@ __attribute__((visibility("default"))) int ba_shim_run(const ba_engine_desc* des
     std::vector<std::vector<freq_t> > freqs(device_count);
     std::vector<std::vector<size_t> > bins(device_count);
     g_cfg.assign(device_count, std::vector<ba_channel_desc>());
+    g_devcfg.assign(desc->devices, desc->devices + device_count);
     g_taken.assign(device_count, std::vector<Taken>());
     for (int i = 0; i < device_count; i++) {
         const ba_device_desc& dd = desc->devices[i];
