@@ -205,6 +205,9 @@ static inline T __shfl_up_sync(unsigned, T v, unsigned d, int = 32) {
     const int lane = emu::tls().tid.x & 31;
     return emu_exchange(v, lane >= (int)d ? lane - (int)d : lane);
 }
+static inline int __clz(int x) {
+    return x == 0 ? 32 : __builtin_clz((unsigned)x);
+}
 static inline unsigned __ballot_sync(unsigned, int pred) {
     unsigned bits = 0;
     for (int l = 0; l < 32; l++)
