@@ -475,6 +475,11 @@ int choose_tiles(ba_engine* e) {
     }
     if (const char* v = getenv("BA_CUDA_K1_TILE"))
         tf = std::max(groups, atoi(v) / groups * groups);
+    if (ba::k1_direct(N)) { /* frames are read straight from global memory: a tile only amortises the hand-over */
+        e->tile_frames = getenv("BA_CUDA_K1_TILE") ? tf : 4;
+        e->raw_bytes = 0;
+        return BA_OK;
+    }
     while (tf > groups && (size_t)fixed + 2 * raw_of(tf) > (size_t)budget)
         tf -= groups;
     while (tf > 1 && (size_t)fixed + 2 * raw_of(tf) > (size_t)e->smem_optin)

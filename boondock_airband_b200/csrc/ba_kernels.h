@@ -72,6 +72,7 @@ int k1_smem_bytes(int fft_size, int raw_bytes, int max_channels);
 int k1_threads(int fft_size);
 int k1_groups(int fft_size); /* FFTs a CTA works on at a time */
 int k1_ctas_per_sm(int fft_size); /* resident CTAs per SM the plan's register cap is chosen for */
+int k1_direct(int fft_size);      /* 1: frames are read straight from global memory (no tile staging in shared memory: raw_bytes = 0) */
 
 /* ------------------------------------------------------------------ K2 */
 

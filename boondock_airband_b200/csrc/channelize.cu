@@ -43,6 +43,11 @@ struct Plan;
         static constexpr int THREADS = T_; /* threads per CTA */                            \
         static constexpr int REGS = REGS_; /* register cap */                               \
         static constexpr int CTAS = CTAS_; /* resident CTAs per SM the cap is chosen for */ \
+        /* N = 8192: the 32 window values and 2 x 31 twiddles of a thread would take 156 registers and leave room for one CTA of  \
+         * eight warps per SM; they are read through L1 where they are used instead, the frames are read straight from global     \
+         * memory (a frame is 64 KB of cf32: staging tiles of them in shared memory is what kept a second CTA out), and two CTAs  \
+         * are resident */                                                                   \
+        static constexpr bool DIRECT = (N_ == 8192);                                         \
         static constexpr int P = P_;                                                        \
         static constexpr int r(int i) { return i == 0 ? A : (i == 1 ? B : (i == 2 ? C : D)); } \
     };
@@ -54,7 +59,7 @@ BA_PLAN(512, 32, 128, 168, 3, 2, 32, 16, 1, 1)
 BA_PLAN(1024, 32, 128, 224, 2, 2, 32, 32, 1, 1)
 BA_PLAN(2048, 16, 256, 112, 2, 3, 8, 16, 16, 1)
 BA_PLAN(4096, 16, 256, 112, 2, 3, 16, 16, 16, 1)
-BA_PLAN(8192, 32, 256, 255, 1, 3, 32, 16, 16, 1)
+BA_PLAN(8192, 32, 256, 128, 2, 3, 32, 16, 16, 1)
 
 template <int N>
 struct Geo {
@@ -316,17 +321,24 @@ __device__ __forceinline__ float2 load_sample(const unsigned char* frame, int n,
     }
 }
 
-/* per-thread constants that do not depend on the frame */
-template <int N>
+/* per-thread constants that do not depend on the frame: in registers, or (Plan::DIRECT) where to read them */
+template <int N, bool DIRECT = Plan<N>::DIRECT>
 struct ThreadConst {
     float win[Geo<N>::V];
     float2 tw[Geo<N>::P - 1][Geo<N>::V - 1];
+};
+template <int N>
+struct ThreadConst<N, true> {
+    const float* window;  /* [N] */
+    const float2* table;  /* [N] exp(-2 pi i n / N) */
 };
 
 template <int N, int PASS>
 __device__ __forceinline__ void twiddle_setup(ThreadConst<N>& tc, const float2* __restrict__ table, int t, int rot) {
     using GE = Geo<N>;
-    if constexpr (PASS < GE::P) {
+    if constexpr (Plan<N>::DIRECT) {
+        tc.table = table;
+    } else if constexpr (PASS < GE::P) {
         constexpr int R = GE::R(PASS);
         constexpr int NB = GE::V / R;
         constexpr int Mp = GE::M(PASS);       /* positions per block after this pass */
@@ -368,7 +380,12 @@ __device__ __forceinline__ void fft_pass(const ThreadConst<N>& tc, float2* __res
                     const int rot = grp & 1;
                     n += rot * Mp - ((j == R - 1) ? rot * R * Mp : 0);
                 }
-                x[i][j] = load_sample<N, FMT>(frame, n, tc.win[i * R + j], scale);
+                float w;
+                if constexpr (Plan<N>::DIRECT)
+                    w = __ldg(tc.window + n);
+                else
+                    w = tc.win[i * R + j];
+                x[i][j] = load_sample<N, FMT>(frame, n, w, scale);
                 if (dbg_in)
                     dbg_in[n] = x[i][j];
             } else {
@@ -378,18 +395,59 @@ __device__ __forceinline__ void fft_pass(const ThreadConst<N>& tc, float2* __res
     }
     /* every load of this pass (and every read of the previous frame's spectrum) precedes the stores below */
     group_sync<N>(grp);
+    if constexpr (Plan<N>::DIRECT && !LAST) {
+        /* Twiddles made in registers: W^(k m), k = 1 .. R-1, is the product of W^(2^b m) over the set bits b of k; the log2 R base
+         * powers come from the table (each correctly rounded), so a twiddle is at most log2 R - 1 complex products away from
+         * exact values.  Reading all of them through L1 instead made the load/store pipe the bound of this kernel (83 % of its
+         * wavefront rate, most of it scattered twiddle sectors) while the FMA pipe idled at 27 %.  The blocks of a thread share
+         * m (G is a multiple of the block length), so one set serves them all. */
+        static_assert(GE::G % Mp == 0, "the blocks of a thread share their twiddles");
+        constexpr int LR = (R == 32) ? 5 : ((R == 16) ? 4 : ((R == 8) ? 3 : ((R == 4) ? 2 : 1)));
+        const int m = t % Mp;
+        float2 base[LR];
 #pragma unroll
-    for (int i = 0; i < NB; i++) {
-        const int u = t + GE::G * i;
-        const int q = u / Mp, m = u % Mp;
-        Dft<R>::run(x[i]);
+        for (int b = 0; b < LR; b++)
+            base[b] = __ldg(tc.table + ((m * GE::Q(PASS - 1)) << b));
 #pragma unroll
-        for (int k = 0; k < R; k++) {
-            if (LAST) {
-                work[k * (N / R) + q] = x[i][k];
-            } else {
-                const float2 v = (k == 0) ? x[i][0] : cmul(x[i][k], tc.tw[PASS - 1][i * (R - 1) + (k - 1)]);
-                work[GE::at(PASS, q * R + k, m)] = v;
+        for (int i = 0; i < NB; i++)
+            Dft<R>::run(x[i]);
+        float2 pw[R];
+#pragma unroll
+        for (int k = 1; k < R; k++) {
+            const int rest = k & (k - 1); /* k without its lowest set bit */
+            const int low = (k & 1) ? 0 : ((k & 2) ? 1 : ((k & 4) ? 2 : ((k & 8) ? 3 : 4))); /* its position */
+            pw[k] = rest == 0 ? base[low] : cmul(pw[rest], base[low]);
+#pragma unroll
+            for (int i = 0; i < NB; i++) {
+                const int u = t + GE::G * i;
+                work[GE::at(PASS, (u / Mp) * R + k, m)] = cmul(x[i][k], pw[k]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NB; i++) {
+            const int u = t + GE::G * i;
+            work[GE::at(PASS, (u / Mp) * R, m)] = x[i][0];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NB; i++) {
+            const int u = t + GE::G * i;
+            const int q = u / Mp, m = u % Mp;
+            Dft<R>::run(x[i]);
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                if (LAST) {
+                    work[k * (N / R) + q] = x[i][k];
+                } else {
+                    float2 v = x[i][0];
+                    if (k != 0) {
+                        if constexpr (Plan<N>::DIRECT)
+                            v = cmul(x[i][k], __ldg(tc.table + k * m * GE::Q(PASS - 1)));
+                        else
+                            v = cmul(x[i][k], tc.tw[PASS - 1][i * (R - 1) + (k - 1)]);
+                    }
+                    work[GE::at(PASS, q * R + k, m)] = v;
+                }
             }
         }
     }
@@ -462,6 +520,7 @@ __device__ __forceinline__ void run_tile_frames(const ThreadConst<N>& tc, const 
 template <int N, bool DBG>
 __global__ void __maxnreg__(Plan<N>::REGS) channelize_kernel(K1Params p) {
     using GE = Geo<N>;
+    static_assert(!Plan<N>::DIRECT, "this size runs channelize_direct_kernel");
     BA_SHARED(smem);
     float2* work_all = reinterpret_cast<float2*>(smem + 2 * (size_t)p.raw_bytes);
     uint16_t* picktab = reinterpret_cast<uint16_t*>(work_all + GE::W * GE::WORK);
@@ -591,12 +650,89 @@ __global__ void __maxnreg__(Plan<N>::REGS) channelize_kernel(K1Params p) {
     }
 }
 
+/* N = 8192 (Plan::DIRECT): one FFT per CTA of 256 threads at a time, frames read straight from global memory (consecutive
+ * lanes read consecutive samples of a first-pass row: 256 coalesced bytes of cf32 per load; frames overlap, so all but the
+ * first touch of a byte is an L2 hit), window and twiddles through L1.  Shared memory holds only the exchange buffer, 128
+ * registers per thread: two or three CTAs per SM instead of one.  Tiles come off the launch-wide counter as above. */
+template <int N, bool DBG>
+__global__ void __maxnreg__(Plan<N>::REGS) channelize_direct_kernel(K1Params p) {
+    using GE = Geo<N>;
+    static_assert(GE::W == 1, "one FFT group per CTA");
+    BA_SHARED(smem);
+    float2* work = reinterpret_cast<float2*>(smem);
+    uint16_t* picktab = reinterpret_cast<uint16_t*>(work + GE::WORK);
+    int* s_tile = reinterpret_cast<int*>(picktab + ((p.max_channels + 7) & ~7));
+    const int t = threadIdx.x;
+    ThreadConst<N> tc;
+    tc.window = p.window;
+    tc.table = p.twiddle;
+    int cur_dev = -1;
+    for (;;) {
+        __syncthreads(); /* everybody is done with s_tile and with the pick table of the tile before */
+        if (t == 0)
+            *s_tile = (int)atomicAdd(p.tile_counter, 1u);
+        __syncthreads();
+        const int tile = *s_tile;
+        if (tile >= p.n_tiles)
+            break;
+        int lo = 0, hi = p.n_dev - 1; /* input that owns this tile: last device with tile0 <= tile */
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (p.dev[mid].tile0 <= (uint32_t)tile)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        const K1Device* dg = p.dev + lo;
+        TileCtx c;
+        c.hop_bytes = dg->hop_bytes;
+        c.n_frames = dg->n_frames;
+        c.ring_mask = dg->ring_mask;
+        c.ring_len = dg->ring_mask + 1;
+        c.n_channels = dg->n_channels;
+        c.frame0 = dg->frame0;
+        c.picks = dg->picks;
+        c.mags = dg->mags;
+        c.scale = dg->scale;
+        const int fmt = dg->fmt;
+        const int f0 = (tile - (int)dg->tile0) * p.tile_frames;
+        const int nf = min(p.tile_frames, (int)c.n_frames - f0);
+        if (lo != cur_dev) { /* uniform over the CTA */
+            const uint32_t* bins = dg->bins;
+            for (int ch = t; ch < (int)c.n_channels; ch += GE::THREADS)
+                picktab[ch] = (uint16_t)GE::out_pos((int)(bins[ch] & (N - 1)));
+            cur_dev = lo;
+            __syncthreads();
+        }
+        const unsigned char* raw0 = dg->iq + (size_t)f0 * c.hop_bytes;
+        switch (fmt) {
+            case BA_SFMT_U8:
+                run_tile_frames<N, BA_SFMT_U8, DBG>(tc, c, dg, raw0, work, picktab, f0, nf, t, 0);
+                break;
+            case BA_SFMT_S8:
+                run_tile_frames<N, BA_SFMT_S8, DBG>(tc, c, dg, raw0, work, picktab, f0, nf, t, 0);
+                break;
+            case BA_SFMT_S16:
+                run_tile_frames<N, BA_SFMT_S16, DBG>(tc, c, dg, raw0, work, picktab, f0, nf, t, 0);
+                break;
+            default:
+                run_tile_frames<N, BA_SFMT_F32, DBG>(tc, c, dg, raw0, work, picktab, f0, nf, t, 0);
+                break;
+        }
+    }
+}
+
 template <int N, bool DBG>
 int launch_n(const K1Params& p, int n_ctas, cudaStream_t s) {
     using GE = Geo<N>;
     const size_t smem = (size_t)k1_smem_bytes(N, p.raw_bytes, p.max_channels);
-    auto kern = channelize_kernel<N, DBG>;
-    BA_LAUNCH(kern, n_ctas, GE::THREADS, smem, s, p);
+    if constexpr (Plan<N>::DIRECT) {
+        auto kern = channelize_direct_kernel<N, DBG>;
+        BA_LAUNCH(kern, n_ctas, GE::THREADS, smem, s, p);
+    } else {
+        auto kern = channelize_kernel<N, DBG>;
+        BA_LAUNCH(kern, n_ctas, GE::THREADS, smem, s, p);
+    }
     return (int)cudaGetLastError();
 }
 
@@ -605,9 +741,16 @@ int launch_n(const K1Params& p, int n_ctas, cudaStream_t s) {
  * through a process-wide flag (one process may drive one engine per GPU, boondock_airband.cpp:1088-1122). */
 template <int N>
 int configure_n(size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(channelize_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(channelize_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e;
+    if constexpr (Plan<N>::DIRECT) {
+        e = cudaFuncSetAttribute(channelize_direct_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(channelize_direct_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    } else {
+        e = cudaFuncSetAttribute(channelize_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(channelize_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
     return (int)e;
 }
 
@@ -674,6 +817,8 @@ int k1_groups(int n) {
 int k1_smem_bytes(int n, int raw_bytes, int max_channels) {
     return 2 * raw_bytes + 8 * k1_groups(n) * (n + n / 8) + 2 * ((max_channels + 7) & ~7) + 64;
 }
+/* sizes whose frames are read straight from global memory: no tile staging, raw_bytes = 0 */
+int k1_direct(int n) { return n == 8192 ? 1 : 0; }
 
 int k1_configure(int fft_size, int raw_bytes, int max_channels) {
     const size_t smem = (size_t)k1_smem_bytes(fft_size, raw_bytes, max_channels);

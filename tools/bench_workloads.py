@@ -29,11 +29,19 @@ def workloads():
         "cfg2x64": ("64 inputs of cfg2's shape on one GPU (2048 NFM/CTCSS channels)", lambda: _replicate(configs.cfg2(), 64)),
         "cfg3": ("8 of the 64 synthetic dongles (one GPU's share): 2.4 Msps u8, fft 512, 16 AM channels each", lambda: configs.cfg3(8)),
         "cfg4": ("wideband: 1 input, 61.44 Msps cf32, fft 8192, 2000 mixed AM/NFM channels (250 with CTCSS + notch)", configs.cfg4),
+        "cfg4_k1": ("cfg4's input with only 64 of its channels: the wideband channelizer (fft 8192, cf32) on its own", _cfg4_few),
         "cfg3_mixers": ("cfg3's 8 inputs with 17 mixers summed on the GPU (K3): mixer k = channel k of every input, plus one stereo mixer over input 0", _cfg3_mixers),
         "cfg5_n1024": ("cfg5 at fft 1024: 512 inputs x 2.56 Msps u8, 16 AM channels", lambda: configs.cfg5(512, 1024)),
         "cfg5_n2048": ("cfg5 at fft 2048", lambda: configs.cfg5(512, 2048)),
         "cfg5_n4096": ("cfg5 at fft 4096", lambda: configs.cfg5(512, 4096)),
     }
+
+
+def _cfg4_few():
+    from boondock_airband_b200 import configs
+    cfg = configs.cfg4()
+    cfg.devices[0].channels = cfg.devices[0].channels[::32][:64]
+    return cfg
 
 
 def _cfg3_mixers():
