@@ -205,6 +205,9 @@ static inline T __shfl_up_sync(unsigned, T v, unsigned d, int = 32) {
     const int lane = emu::tls().tid.x & 31;
     return emu_exchange(v, lane >= (int)d ? lane - (int)d : lane);
 }
+static inline int __popc(unsigned x) {
+    return __builtin_popcount(x);
+}
 static inline int __clz(int x) {
     return x == 0 ? 32 : __builtin_clz((unsigned)x);
 }
