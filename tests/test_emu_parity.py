@@ -161,3 +161,51 @@ def test_emu_results_do_not_depend_on_how_the_stream_is_cut(emu):
     assert runs[0].shape == runs[1].shape == runs[2].shape and runs[0].shape[1] >= 2 * cfg.wave_batch
     assert np.array_equal(runs[0].view(np.uint32), runs[2].view(np.uint32))
     assert np.array_equal(runs[1].view(np.uint32), runs[2].view(np.uint32))
+
+
+def test_emu_two_engines_on_two_devices_in_one_process(emu, monkeypatch):
+    """One engine per GPU inside one process (one demod thread per device, boondock_airband.cpp:1088-1122): the kernels'
+    dynamic shared-memory limit is an attribute of the (device, function) pair, so an engine created on a second device must set
+    it there itself.  The emulation refuses a launch whose limit was not set on the current device; the two engines run
+    interleaved from one thread, so every entry point has to select its own device."""
+    import threading
+    from boondock_airband_b200.engine import Engine
+    monkeypatch.setenv("BA_EMU_DEVICES", "2")
+    cfg, streams = scenarios.cfg1_short(0.5)
+    cfgs = []
+    for dev in (0, 1):
+        c, _ = scenarios.cfg1_short(0.5)
+        c.cuda_device = dev
+        cfgs.append(c)
+    engines = [Engine(c, emu) for c in cfgs]
+    try:
+        res = [None, None]
+        # interleaved from ONE thread first (the current device must follow the engine that is called) ...
+        views = np.ascontiguousarray(streams[0]).view(np.uint8).reshape(-1)
+        half = views.size // 2
+        accs = [e._new_acc() for e in engines]
+        for part in (views[:half], views[half:]):
+            for e, acc in zip(engines, accs):
+                e.submit(0, part)
+                while True:
+                    produced, advanced = e._step_into(acc)
+                    if not produced and not advanced:
+                        break
+        res = [e._finish_acc(acc) for e, acc in zip(engines, accs)]
+        # ... then one engine per thread, as the reference's demod threads would
+        out = [None, None]
+
+        def work(k):
+            out[k] = engines[k].launch_count()
+        th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert out[0] > 0 and out[1] > 0
+    finally:
+        for e in engines:
+            e.close()
+    a, b = res[0][0]["waveout"], res[1][0]["waveout"]
+    assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert res[0][0]["frames_done"] == res[1][0]["frames_done"] > 0

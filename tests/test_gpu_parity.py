@@ -504,3 +504,24 @@ def test_results_on_device_equal_results_on_host(cuda):
         e.close()
     got = np.concatenate(waves, axis=1)
     assert np.array_equal(got.view(np.uint32), res[0]["waveout"].view(np.uint32))
+
+
+def test_two_engines_on_two_gpus_in_one_process(cuda):
+    """One engine per GPU inside one process (boondock_airband.cpp:1088-1122: one demod thread per device).  Skipped on a box
+    with a single GPU."""
+    from boondock_airband_b200 import engine as eng_mod
+    if int(eng_mod.load_library().ba_cuda_visible_devices()) < 2:
+        pytest.skip("needs two GPUs")
+    cfg0, streams = scenarios.cfg1_short(0.9)
+    cfg1, _ = scenarios.cfg1_short(0.9)
+    cfg1.cuda_device = 1
+    e0, e1 = Engine(cfg0, cuda), Engine(cfg1, cuda)
+    try:
+        r1 = e1.run_stream(streams, chunk_bytes=500_000)
+        r0 = e0.run_stream(streams, chunk_bytes=700_001)
+    finally:
+        e0.close()
+        e1.close()
+    for c in range(len(cfg0.devices[0].channels)):
+        assert np.array_equal(r0[0]["waveout"][c].view(np.uint32), r1[0]["waveout"][c].view(np.uint32))
+    assert r0[0]["frames_done"] == r1[0]["frames_done"] > 0

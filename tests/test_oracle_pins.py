@@ -382,3 +382,47 @@ def test_u8_level_formula():
         assert got == want, code
         # and the table the reference fills is what numpy's float32 division gives
         assert float(want) == float(np.float32(code - 127.5) / np.float32(127.5))
+
+
+def _mix_with_restatement(orc, ampfactor, balance, x, has_signal):
+    """oracle/ba_oracle.py: mix_reference on explicit batches (input j = channel 0 of a pretend device j)."""
+    from boondock_airband_b200.abi import MixerCfg, MixerInputCfg
+    n_b, n_in, B = x.shape
+    cfg = EngineCfg(fft_size=512, wave_rate=8 * B, devices=[])
+    mixer = MixerCfg("pin", [MixerInputCfg(j, 0, ampfactor=float(ampfactor[j]), balance=float(balance[j])) for j in range(n_in)])
+
+    class St:
+        def __init__(self, a):
+            self.axcindicate = a
+    wave = lambda d, c: np.ascontiguousarray(x[:, d, :]).reshape(-1)
+    stat = lambda d, c: [St(abi.SIGNAL if has_signal[k, d] else abi.NO_SIGNAL) for k in range(n_b)]
+    return orc.mix_reference(cfg, wave, stat, mixer)
+
+
+def test_mixer_restatement_against_a_run_of_the_reference_mixer(orc):
+    """tests/golden/golden_mixer.npz was produced by the reference's own mixer.cpp (mixer_connect_input, mixer_put_samples,
+    mixer_thread; tests/golden/make_golden_mixer.py).  The restated summing the device-side mixer is compared with
+    (oracle/ba_oracle.py: mix_reference) reproduces it bit for bit: multipliers ampfactor * min(1, 1 -/+ balance), inputs without
+    signal skipped, a zero multiplier skipped, stereo as soon as one balance is non-zero, SIGNAL iff any input had signal."""
+    g = np.load(os.path.join(GOLD, "golden_mixer.npz"))
+    left, right, sig = _mix_with_restatement(orc, g["ampfactor"], g["balance"], g["x"], g["has_signal"])
+    assert int(g["stereo"]) == 1 and right is not None
+    assert np.array_equal(left.view(np.uint32), g["left"].reshape(-1).view(np.uint32))
+    assert np.array_equal(right.view(np.uint32), g["right"].reshape(-1).view(np.uint32))
+    want = np.where(g["axcindicate"] == ord("*"), abi.SIGNAL, abi.NO_SIGNAL)
+    assert list(sig) == list(want)
+    assert (g["axcindicate"] == ord(" ")).any() and (g["left"][2] == 0).all()  # the batch in which nobody had signal
+
+
+def test_reference_mixer_reproduces_the_fixture(orc):
+    """Where the reference tree is mounted: the committed fixture is what its mixer produces today."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_mixer", os.path.join(GOLD, "make_golden_mixer.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    if not (orc.have_ref() and os.path.exists(mg.LIB)):
+        pytest.skip("oracle/_ref/libba_mixer_ref.so is not built (needs /root/reference)")
+    a, b, x, s = mg.case()
+    left, right, axc, stereo = mg.run_reference(a, b, x, s)
+    g = np.load(os.path.join(GOLD, "golden_mixer.npz"))
+    assert np.array_equal(left, g["left"]) and np.array_equal(right, g["right"]) and np.array_equal(axc, g["axcindicate"]) and stereo == int(g["stereo"])
