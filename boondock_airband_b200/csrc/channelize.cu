@@ -25,6 +25,7 @@
 #include <stdint.h>
 
 #include "ba_kernels.h"
+#include "ba_f32x2.h"
 
 namespace ba {
 namespace {
@@ -110,41 +111,7 @@ struct Geo {
  * subtract is ONE instruction, a multiply by -j is free, and a complex multiply is FMUL2 + FFMA2.  The kernel is bound by
  * instruction issue (profiles/): this halves the FP32 instruction count of the butterflies, twiddles and the sample
  * conversion.  Every component is still an individually rounded IEEE operation (the conversions stay bit-exact). */
-#ifdef BA_EMU
-__device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
-#else
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-    float2 r;
-    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
-        : "=f"(r.x), "=f"(r.y)
-        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return r;
-}
-__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
-    float2 r;
-    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
-        : "=f"(r.x), "=f"(r.y)
-        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return r;
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-    float2 r;
-    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
-        : "=f"(r.x), "=f"(r.y)
-        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return r;
-}
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-    float2 r;
-    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
-        : "=f"(r.x), "=f"(r.y)
-        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-    return r;
-}
-#endif
+/* (add2 / sub2 / mul2 / fma2: ba_f32x2.h) */
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return add2(a, b); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return sub2(a, b); }
 /* (a.x b.x - a.y b.y, a.y b.x + a.x b.y) = (-a.y, a.x) * b.y + a * b.x */
