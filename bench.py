@@ -290,7 +290,7 @@ def main():
               "inputs_per_gpu": args.inputs, "sample_rate": FS, "sample_format": "u8", "fft_size": args.fft_size, "channels_per_input": N_CHANNELS,
               "wave_rate": WAVE_RATE, "samples_per_step_per_gpu": step_samples, "parallelism": "inputs sharded over GPUs, no collective",
               "l2": "inputs larger than L2 (%.2f GB of fresh IQ per step)" % (2 * step_samples / 1e9),
-              "results": "value: IQ resident in HBM, audio copied to pinned host memory; value_results_on_device: audio stays in HBM (BA_FLAG_RESULTS_ON_DEVICE), status returns to the host; e2e: host copies both ways"}
+              "results": "value: IQ resident in HBM, audio copied to pinned host memory; value_skip_silent_rows: the same, (channel, batch) rows of exact zeros left out of the copy (BA_FLAG_SKIP_SILENT_ROWS); value_results_on_device: audio stays in HBM (BA_FLAG_RESULTS_ON_DEVICE), status returns to the host; e2e: host copies both ways"}
 
     import torch
 
@@ -365,6 +365,7 @@ def main():
         tickets = []
 
         copy_legs = [0.0, 0.0]
+        d2h_total = [0]
 
         def run_steps(n, first):
             k1 = k2 = 0.0
@@ -384,6 +385,7 @@ def main():
                     h, d = eng.copy_ms(old)
                     copy_legs[0] += h
                     copy_legs[1] += d
+                    d2h_total[0] += eng.step_bytes(old)[1]
                     batches += r.n_batches
             while tickets:
                 old = tickets.pop(0)
@@ -394,11 +396,13 @@ def main():
                 h, d = eng.copy_ms(old)
                 copy_legs[0] += h
                 copy_legs[1] += d
+                d2h_total[0] += eng.step_bytes(old)[1]
                 batches += r.n_batches
             return k1, k2, batches
 
         run_steps(W, True)
         copy_legs[0] = copy_legs[1] = 0.0
+        d2h_total[0] = 0
         launches0 = eng.launch_count()
         barrier()
         eng.mark(0)
@@ -419,7 +423,7 @@ def main():
             elapsed = sharding.max_over_ranks(elapsed, dist, device)
             wall = sharding.max_over_ranks(wall, dist, device)
         eng.close()
-        return {"elapsed": elapsed, "wall": wall, "dev_ms": dev_ms, "k1_ms": k1_ms, "k2_ms": k2_ms, "launches": launches, "copy_legs": list(copy_legs)}
+        return {"elapsed": elapsed, "wall": wall, "dev_ms": dev_ms, "k1_ms": k1_ms, "k2_ms": k2_ms, "launches": launches, "copy_legs": list(copy_legs), "d2h_bytes": d2h_total[0]}
 
     # `value`: IQ resident in HBM, the demodulated audio copied to pinned host memory inside the timed region (the data flow
     # BASELINE.json names).  The same run with the results left in HBM for a consumer on the GPU (BA_FLAG_RESULTS_ON_DEVICE:
@@ -428,6 +432,9 @@ def main():
     from boondock_airband_b200 import abi as _abi
     leg_dev = device_leg(_abi.FLAG_RESULTS_ON_DEVICE)
     leg_host = device_leg(0)
+    # the same as `value`, but only the (channel, batch) rows that are not silence cross the link (BA_FLAG_SKIP_SILENT_ROWS: decided on
+    # the data on the device; the synthetic carriers are keyed 1.5 s on / 0.5 s off, so about a quarter of the rows are silence)
+    leg_skip = device_leg(_abi.FLAG_SKIP_SILENT_ROWS)
     elapsed, wall, dev_ms, k1_ms, k2_ms, launches, copy_legs = (leg_host[k] for k in ("elapsed", "wall", "dev_ms", "k1_ms", "k2_ms", "launches", "copy_legs"))
     # strong scaling (N > 1): BASELINE.json's cfg5 is 512 inputs in total; input i of the job runs on GPU i mod G
     strong = None
@@ -589,6 +596,8 @@ def main():
             "results_d2h_ms_per_step": copy_legs[1] / K,
             "value_results_on_device": value_dev, "ms_per_step_results_on_device": 1e3 * leg_dev["elapsed"] / K,
             "value_results_on_device_kernels_ms_per_step": {"channelize(K1)": leg_dev["k1_ms"] / K, "demod(K2)": leg_dev["k2_ms"] / K},
+            "value_skip_silent_rows": sharding.aggregate_msps(world, K, step_samples, leg_skip["elapsed"]), "ms_per_step_skip_silent_rows": 1e3 * leg_skip["elapsed"] / K,
+            "d2h_bytes_per_step": leg_host["d2h_bytes"] // K, "d2h_bytes_per_step_skip_silent_rows": leg_skip["d2h_bytes"] // K,
             "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic (%d seeded streams, a private HBM copy per input)" % TEMPLATES, "config": config,
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline}

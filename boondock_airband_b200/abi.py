@@ -13,7 +13,7 @@ import ctypes as C
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 SFMT = {"u8": 1, "s8": 2, "s16": 3, "f32": 4}
 SFMT_BYTES = {"u8": 1, "s8": 1, "s16": 2, "f32": 4}
@@ -25,6 +25,7 @@ SQ_CLOSED, SQ_OPENING, SQ_CLOSING, SQ_LOW_SIGNAL_ABORT, SQ_OPEN = range(5)
 FLAG_TRACE = 0x1
 FLAG_KEEP_PICKS = 0x2
 FLAG_RESULTS_ON_DEVICE = 0x4
+FLAG_SKIP_SILENT_ROWS = 0x8
 TRACE_STATE_MASK, TRACE_OPEN, TRACE_AUDIO, TRACE_FILTERED = 0x07, 0x08, 0x10, 0x20
 
 OK = 0
@@ -141,6 +142,10 @@ class StepOut(C.Structure):
         ("trace", C.POINTER(C.c_uint8)),
         ("status", C.POINTER(ChannelStatus)),
         ("frames_done", C.c_uint64),
+        ("rows", C.POINTER(C.c_float)),
+        ("row_of", C.POINTER(C.c_int32)),
+        ("n_rows", C.c_uint32),
+        ("row_of_stride", C.c_int32),
     ]
 
 

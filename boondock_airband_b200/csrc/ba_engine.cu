@@ -139,6 +139,16 @@ struct Slot {
     std::vector<uint64_t> mix_first;  /* and the number of the first of them */
     float* d_wave = nullptr;
     float* h_wave = nullptr;
+    /* BA_FLAG_SKIP_SILENT_ROWS: packed non-silent rows, the row map, the row counter, the per-device row table the pack kernel reads */
+    float* d_pack = nullptr;
+    float* h_pack = nullptr;
+    int32_t* d_rowmap = nullptr;
+    int32_t* h_rowmap = nullptr;
+    uint32_t* d_rowcount = nullptr;
+    uint32_t* h_rowcount = nullptr;
+    ba::K3PackDev* h_packdev = nullptr;
+    bool pack_pending = false; /* the rows of this ticket have not been fetched yet (the first ba_cuda_collect() does it) */
+    uint32_t pack_rows = 0;
     float2* d_iq = nullptr;
     float2* h_iq = nullptr;
     uint8_t* d_trace = nullptr;
@@ -187,6 +197,7 @@ struct ba_engine {
     cudaStream_t stream = nullptr; /* = s_k: kernels; debug helpers run here */
     cudaStream_t s_in = nullptr, s_k = nullptr, s_k2 = nullptr, s_out = nullptr; /* host->device, K1, K2, device->host */
     cudaStream_t s_k2b = nullptr; /* the plain-AM demodulator runs here beside the general one */
+    cudaStream_t s_pack = nullptr; /* BA_FLAG_SKIP_SILENT_ROWS: ba_cuda_collect() fetches a ticket's packed rows here (its own stream: later tickets queue on s_out) */
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t s_in2 = nullptr; /* second host->device stream: alternate inputs, so that one copy's set-up hides behind the other's transfer */
     int h2d_streams = 2;
@@ -231,7 +242,7 @@ void free_engine(ba_engine* e) {
     if (!e)
         return;
     cudaSetDevice(e->cuda_device);
-    for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2, e->s_k2b, e->s_out})
+    for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2, e->s_k2b, e->s_out, e->s_pack})
         if (q)
             cudaStreamSynchronize(q);
     for (Dev* d : e->dev) {
@@ -261,6 +272,17 @@ void free_engine(ba_engine* e) {
         if (s.h_mix_sig)
             cudaFreeHost(s.h_mix_sig);
         cudaFree(s.d_wave);
+        cudaFree(s.d_pack);
+        cudaFree(s.d_rowmap);
+        cudaFree(s.d_rowcount);
+        if (s.h_pack)
+            cudaFreeHost(s.h_pack);
+        if (s.h_rowmap)
+            cudaFreeHost(s.h_rowmap);
+        if (s.h_rowcount)
+            cudaFreeHost(s.h_rowcount);
+        if (s.h_packdev)
+            cudaFreeHost(s.h_packdev);
         cudaFree(s.d_iq);
         cudaFree(s.d_trace);
         cudaFree(s.d_status);
@@ -307,7 +329,7 @@ void free_engine(ba_engine* e) {
     cudaFree(e->d_ctcss);
     cudaFree(e->d_order);
     cudaFree(e->d_tile_counter);
-    for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2, e->s_k2b, e->s_out})
+    for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2, e->s_k2b, e->s_out, e->s_pack})
         if (q)
             cudaStreamDestroy(q);
     for (cudaEvent_t ev : {e->ev_tmp[0], e->ev_tmp[1], e->ev_fork, e->ev_join})
@@ -571,6 +593,7 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
     CU(cudaStreamCreateWithFlags(&e->s_k, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->s_k2, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&e->s_pack, cudaStreamNonBlocking));
     e->stream = e->s_k;
     CU(cudaEventCreateWithFlags(&e->ev_tmp[0], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&e->ev_tmp[1], cudaEventDisableTiming));
@@ -831,6 +854,15 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
                 return fail(BA_ERR_NOMEM, "output arena of %zu floats", wave);
             CU(cudaMemset(s.d_wave, 0, sizeof(float) * wave));
             memset(s.h_wave, 0, sizeof(float) * wave);
+            if (e->flags & BA_FLAG_SKIP_SILENT_ROWS) {
+                const size_t rows = (size_t)e->total_channels * e->max_batches;
+                if (cudaMalloc((void**)&s.d_pack, sizeof(float) * rows * e->B) != cudaSuccess || cudaHostAlloc((void**)&s.h_pack, sizeof(float) * rows * e->B, cudaHostAllocDefault) != cudaSuccess ||
+                    cudaMalloc((void**)&s.d_rowmap, sizeof(int32_t) * rows) != cudaSuccess || cudaHostAlloc((void**)&s.h_rowmap, sizeof(int32_t) * rows, cudaHostAllocDefault) != cudaSuccess ||
+                    cudaMalloc((void**)&s.d_rowcount, sizeof(uint32_t)) != cudaSuccess || cudaHostAlloc((void**)&s.h_rowcount, sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess ||
+                    cudaHostAlloc((void**)&s.h_packdev, sizeof(ba::K3PackDev) * e->dev.size(), cudaHostAllocDefault) != cudaSuccess)
+                    return fail(BA_ERR_NOMEM, "packed-row arena");
+                memset(s.h_rowmap, 0xff, sizeof(int32_t) * rows);
+            }
             if (e->any_iq) {
                 if (cudaMalloc((void**)&s.d_iq, sizeof(float2) * wave) != cudaSuccess || cudaHostAlloc((void**)&s.h_iq, sizeof(float2) * wave, cudaHostAllocDefault) != cudaSuccess)
                     return fail(BA_ERR_NOMEM, "iq_out arena");
@@ -1420,6 +1452,34 @@ int ba_cuda_process(ba_engine* e) {
         e->launches += (mix_max_emit > 0 ? 1 : 0) + (mix_max_stash > 0 ? 1 : 0);
     }
 
+    /* 3b. BA_FLAG_SKIP_SILENT_ROWS: pack the rows that are not silence (behind the demodulator and the mixers, which read the arena) */
+    s.pack_pending = false;
+    s.pack_rows = 0;
+    const bool skip_silence = (e->flags & BA_FLAG_SKIP_SILENT_ROWS) && !(e->flags & BA_FLAG_RESULTS_ON_DEVICE);
+    if (skip_silence) {
+        uint32_t rows = 0, ch0 = 0;
+        int n = 0;
+        for (Dev* d : e->dev) {
+            if (d->step_batches > 0) {
+                s.h_packdev[n].first_channel = ch0;
+                s.h_packdev[n].n_channels = (uint32_t)d->C;
+                s.h_packdev[n].n_batches = (uint32_t)d->step_batches;
+                s.h_packdev[n].row0 = rows;
+                rows += (uint32_t)d->C * (uint32_t)d->step_batches;
+                n++;
+            }
+            ch0 += (uint32_t)d->C;
+        }
+        if (rows > 0) {
+            CU(cudaMemsetAsync(s.d_rowcount, 0, sizeof(uint32_t), k2s));
+            int rc = ba::k3_pack_launch(s.h_packdev, n, (int)rows, s.d_wave, e->stride, B, s.d_pack, s.d_rowmap, e->max_batches, s.d_rowcount, k2s);
+            if (rc != 0)
+                return fail(BA_ERR_CUDA, "pack launch: %s", cudaGetErrorString((cudaError_t)rc));
+            e->launches += 1;
+            s.pack_pending = true;
+        }
+    }
+
     CU(cudaEventRecord(s.ev_kdone, k2s));
     CU(cudaStreamWaitEvent(e->s_out, s.ev_kdone, 0));
     CU(cudaEventRecord(s.ev_out0, e->s_out));
@@ -1443,6 +1503,22 @@ int ba_cuda_process(ba_engine* e) {
         };
         const bool to_host = !(e->flags & BA_FLAG_RESULTS_ON_DEVICE); /* else audio, iq_out and trace stay in HBM for a consumer on the GPU */
         if (!to_host) {
+        } else if (skip_silence) {
+            /* the row map and the number of packed rows now; the rows themselves when ba_cuda_collect() knows how many there are */
+            if (s.pack_pending) {
+                const size_t rows = (size_t)e->total_channels * e->max_batches;
+                CU(cudaMemcpyAsync(s.h_rowmap, s.d_rowmap, sizeof(int32_t) * rows, cudaMemcpyDeviceToHost, e->s_out));
+                CU(cudaMemcpyAsync(s.h_rowcount, s.d_rowcount, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->s_out));
+                s.d2h_bytes += sizeof(int32_t) * rows + sizeof(uint32_t);
+                if (s.d_trace) {
+                    for (Dev* d : e->dev)
+                        if (d->step_batches > 0) {
+                            const size_t width = (size_t)d->step_batches * B;
+                            CU(cudaMemcpy2DAsync(s.h_trace + d->wave_off, e->stride, s.d_trace + d->wave_off, e->stride, width, (size_t)d->C, cudaMemcpyDeviceToHost, e->s_out));
+                            s.d2h_bytes += width * d->C;
+                        }
+                }
+            }
         } else if (uniform && nb0 == e->max_batches && !s.d_trace) {
             /* a full step everywhere: one linear copy of the arena (the E carried-over samples per row ride along, 1 %) */
             size_t floats = 0;
@@ -1527,6 +1603,15 @@ int ba_cuda_collect(ba_engine* e, int ticket, int dev, ba_step_out* out) {
         return s && d ? fail(BA_ERR_BAD_ARG, "null out") : BA_ERR_BAD_ARG;
     USE_DEVICE(e);
     CU(cudaEventSynchronize(s->ev_done));
+    if (s->pack_pending) { /* BA_FLAG_SKIP_SILENT_ROWS: now the number of rows is known; one contiguous copy, once per ticket */
+        s->pack_pending = false;
+        s->pack_rows = *s->h_rowcount;
+        if (s->pack_rows > 0) {
+            CU(cudaMemcpyAsync(s->h_pack, s->d_pack, sizeof(float) * (size_t)s->pack_rows * e->B, cudaMemcpyDeviceToHost, e->s_pack));
+            CU(cudaStreamSynchronize(e->s_pack));
+            s->d2h_bytes += sizeof(float) * (size_t)s->pack_rows * e->B;
+        }
+    }
     release_rings(e, false);
     s->busy = false;
     memset(out, 0, sizeof(*out));
@@ -1536,6 +1621,13 @@ int ba_cuda_collect(ba_engine* e, int ticket, int dev, ba_step_out* out) {
     out->wave_stride = e->stride;
     const bool on_dev = (e->flags & BA_FLAG_RESULTS_ON_DEVICE) != 0;
     out->waveout = (on_dev ? s->d_wave : s->h_wave) + d->wave_off;
+    if ((e->flags & BA_FLAG_SKIP_SILENT_ROWS) && !on_dev) {
+        out->waveout = nullptr;
+        out->rows = s->h_pack;
+        out->row_of = s->h_rowmap + (d->wave_off / (size_t)e->stride) * (size_t)e->max_batches;
+        out->n_rows = s->pack_rows;
+        out->row_of_stride = e->max_batches;
+    }
     out->iq_out = (s->h_iq && d->any_iq) ? reinterpret_cast<const float*>((on_dev ? s->d_iq : s->h_iq) + d->iq_off) : nullptr;
     out->trace = s->h_trace ? (on_dev ? s->d_trace : s->h_trace) + d->wave_off : nullptr;
     out->status = s->h_status + d->status_off;
@@ -1724,7 +1816,7 @@ int ba_cuda_debug_frames(ba_engine* e, int dev, const void* iq, size_t bytes, in
             return fail(BA_ERR_CUDA, "%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
         }                                                                                          \
     } while (0)
-    for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2, e->s_k2b, e->s_out})
+    for (cudaStream_t q : {e->s_in, e->s_in2, e->s_k, e->s_k2, e->s_k2b, e->s_out, e->s_pack})
         CUD(cudaStreamSynchronize(q));
     CUD(cudaMalloc((void**)&d_iq, bytes + 16));
     CUD(cudaMalloc((void**)&d_in, sizeof(float2) * N * n_frames));

@@ -204,6 +204,16 @@ struct K3Params {
     uint8_t* fifo_sig; /* [inputs][fifo_depth] */
     int32_t fifo_depth, wave_batch;
 };
+/* BA_FLAG_SKIP_SILENT_ROWS: the rows of one step, device by device */
+struct K3PackDev {
+    uint32_t first_channel, n_channels, n_batches, row0; /* row0: rows of the devices before this one */
+};
+/* one warp per (channel, batch) row of `wave` ([channel][stride], batch b at b * wave_batch): rows holding anything but +0.0f are
+ * copied to pack[slot][wave_batch] (slot from an atomic counter) and rowmap[channel][max_batches] = slot, else -1.
+ * `devs` may live in pinned host memory (read once). */
+int k3_pack_launch(const K3PackDev* devs, int n_dev, int total_rows, const float* wave, int stride, int wave_batch, float* pack, int32_t* rowmap, int max_batches,
+                   uint32_t* count, cudaStream_t s);
+
 /* mixes max_emit (largest n_emit of any mixer) batches, then parks max_stash (largest stash_count) */
 int k3_launch(const K3Params& p, int n_mixers, int max_emit, int n_inputs, int max_stash, cudaStream_t s);
 

@@ -105,6 +105,8 @@ void* demodulate_cuda(void* params) { /* void* demodulate(void* params), boondoc
     ed.device_count = n;
     ed.devices = dd.data();
     ed.max_batches_per_step = max_batches_from_env();
+    if (getenv("BA_CUDA_SKIP_SILENT_ROWS")) /* replays far above real time: silence does not cross the link (see ba_cuda.h) */
+        ed.flags |= BA_FLAG_SKIP_SILENT_ROWS;
     ba_engine* eng = NULL;
     const int ret = ba_cuda_create(&ed, &eng);
     if (ret != BA_OK) { /* the reference's reaction to a failing gpu_fft_prepare(), boondock_airband.cpp:319-332 */
@@ -194,7 +196,15 @@ void* demodulate_cuda(void* params) { /* void* demodulate(void* params), boondoc
                 for (int c = 0; c < dev->channel_count; c++) {
                     channel_t* chn = dev->channels + c;
                     const ba_channel_status* st = out.status + (size_t)b * out.channel_count + c;
-                    memcpy(chn->waveout, out.waveout + (size_t)c * out.wave_stride + (size_t)b * B, B * sizeof(float));
+                    if (out.waveout) {
+                        memcpy(chn->waveout, out.waveout + (size_t)c * out.wave_stride + (size_t)b * B, B * sizeof(float));
+                    } else { /* BA_FLAG_SKIP_SILENT_ROWS: the row, or silence */
+                        const int32_t row = out.row_of[(size_t)c * out.row_of_stride + b];
+                        if (row >= 0)
+                            memcpy(chn->waveout, out.rows + (size_t)row * B, B * sizeof(float));
+                        else
+                            memset(chn->waveout, 0, B * sizeof(float));
+                    }
                     if (out.iq_out && chn->has_iq_outputs)
                         memcpy(chn->iq_out, out.iq_out + 2 * ((size_t)c * out.wave_stride + (size_t)b * B), 2 * B * sizeof(float));
                     chn->axcindicate = (status)st->axcindicate;

@@ -95,7 +95,70 @@ __global__ void __launch_bounds__(128) stash_kernel(K3Params p) {
         p.fifo_sig[(size_t)fi * p.fifo_depth + slot] = sig ? 1 : 0;
 }
 
+/* BA_FLAG_SKIP_SILENT_ROWS: HBM-bound elementwise work (every audio sample is read once, the rows that are kept written once) */
+__global__ void __launch_bounds__(256) pack_rows_kernel(const K3PackDev* devs, int n_dev, int total_rows, const float* wave, int stride, int B, float* pack, int32_t* rowmap,
+                                                        int max_batches, uint32_t* count) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= total_rows)
+        return;
+    int lo = 0, hi = n_dev - 1; /* device that owns row r: last one with row0 <= r */
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (devs[mid].row0 <= (uint32_t)r)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const K3PackDev d = devs[lo];
+    const uint32_t local = (uint32_t)r - d.row0;
+    const uint32_t ch = d.first_channel + local / d.n_batches, b = local % d.n_batches;
+    const float4* src = reinterpret_cast<const float4*>(wave + (size_t)ch * stride + (size_t)b * B);
+    const int quads = B >> 2;
+    float4 v[8];
+    unsigned bits = 0u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int q = lane + 32 * i;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < quads) {
+            v[i] = src[q];
+            bits |= __float_as_uint(v[i].x) | __float_as_uint(v[i].y) | __float_as_uint(v[i].z) | __float_as_uint(v[i].w);
+        }
+    }
+    for (int q = lane + 256; q < quads; q += 32) { /* (wave_batch above 1024: the rest of the row, checked here, copied below) */
+        const float4 x = src[q];
+        bits |= __float_as_uint(x.x) | __float_as_uint(x.y) | __float_as_uint(x.z) | __float_as_uint(x.w);
+    }
+    const bool any = __any_sync(0xffffffffu, bits != 0u);
+    int slot = -1;
+    if (any) {
+        if (lane == 0)
+            slot = (int)atomicAdd(count, 1u);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        float4* dst = reinterpret_cast<float4*>(pack + (size_t)slot * B);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int q = lane + 32 * i;
+            if (q < quads)
+                dst[q] = v[i];
+        }
+        for (int q = lane + 256; q < quads; q += 32)
+            dst[q] = src[q];
+    }
+    if (lane == 0)
+        rowmap[(size_t)ch * max_batches + b] = slot;
+}
+
 }  // namespace
+
+int k3_pack_launch(const K3PackDev* devs, int n_dev, int total_rows, const float* wave, int stride, int wave_batch, float* pack, int32_t* rowmap, int max_batches,
+                   uint32_t* count, cudaStream_t s) {
+    if (total_rows <= 0)
+        return 0;
+    BA_LAUNCH(pack_rows_kernel, (total_rows + 7) / 8, 256, 0, s, devs, n_dev, total_rows, wave, stride, wave_batch, pack, rowmap, max_batches, count);
+    return (int)cudaGetLastError();
+}
 
 int k3_launch(const K3Params& p, int n_mixers, int max_emit, int n_inputs, int max_stash, cudaStream_t s) {
     const int tiles = (p.wave_batch / 4 + 127) / 128;

@@ -92,9 +92,25 @@ class StepResult:
         self.frames_done = out.frames_done
         n = self.n_batches * self.wave_batch
         c, stride = self.channel_count, out.wave_stride
+        self.rows_skipped = 0
         if n > 0:
-            full = np.ctypeslib.as_array(out.waveout, shape=(c, stride))
-            self.waveout = full[:, :n].copy()
+            if out.waveout:
+                full = np.ctypeslib.as_array(out.waveout, shape=(c, stride))
+                self.waveout = full[:, :n].copy()
+            else:
+                # BA_FLAG_SKIP_SILENT_ROWS: only the rows that are not silence came back, plus where each one goes
+                B = self.wave_batch
+                self.waveout = np.zeros((c, n), np.float32)
+                row_of = np.ctypeslib.as_array(out.row_of, shape=(c, out.row_of_stride))[:, :self.n_batches]
+                rows = np.ctypeslib.as_array(out.rows, shape=(max(1, out.n_rows), B))
+                for ch in range(c):
+                    for b in range(self.n_batches):
+                        r = int(row_of[ch, b])
+                        if r >= 0:
+                            assert r < out.n_rows
+                            self.waveout[ch, b * B:(b + 1) * B] = rows[r]
+                        else:
+                            self.rows_skipped += 1
             self.iq_out = None
             if out.iq_out:
                 iq = np.ctypeslib.as_array(out.iq_out, shape=(c, stride, 2))
@@ -351,6 +367,7 @@ class Engine:
             acc[d]["frames_done"] = r.frames_done
             if r.n_batches:
                 produced = True
+                acc[d]["rows_skipped"] = acc[d].get("rows_skipped", 0) + r.rows_skipped
                 acc[d]["waveout"].append(r.waveout)
                 if r.iq_out is not None:
                     acc[d]["iq_out"].append(r.iq_out)
@@ -387,5 +404,5 @@ class Engine:
                 waveout=np.concatenate(a["waveout"], axis=1) if a["waveout"] else np.zeros((c, 0), np.float32),
                 iq_out=np.concatenate(a["iq_out"], axis=1) if a["iq_out"] else None,
                 trace=np.concatenate(a["trace"], axis=1) if a["trace"] else None,
-                status=a["status"], frames_done=a["frames_done"]))
+                status=a["status"], frames_done=a["frames_done"], rows_skipped=a.get("rows_skipped", 0)))
         return out

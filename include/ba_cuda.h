@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BA_CUDA_ABI_VERSION 2 /* 2: mixers in ba_engine_desc, frequency lists in ba_channel_desc (struct sizes changed: 1 is refused) */
+#define BA_CUDA_ABI_VERSION 3 /* 2: mixers in ba_engine_desc, frequency lists in ba_channel_desc; 3: ba_step_out grew (rows, row_of, n_rows). Older callers are refused */
 
 #if defined(__GNUC__)
 #define BA_API __attribute__((visibility("default")))
@@ -66,6 +66,12 @@ enum { BA_SQ_CLOSED = 0, BA_SQ_OPENING = 1, BA_SQ_CLOSING = 2, BA_SQ_LOW_SIGNAL_
 #define BA_FLAG_RESULTS_ON_DEVICE 0x4u /* for consumers on the GPU (encoders, further DSP): waveout / iq_out / trace of ba_step_out
                                         * and the planes of ba_mixer_out are DEVICE pointers into the ticket's result slot and are not
                                         * copied to the host; status and axcindicate still are.  Valid until three more ba_cuda_process(). */
+#define BA_FLAG_SKIP_SILENT_ROWS 0x8u  /* Far above real time the device->host copy of the audio bounds the path, and a squelched channel's
+                                        * audio is exact zeros.  With this flag the engine looks at every (channel, batch) row of wave_batch
+                                        * samples on the device, packs the rows that hold anything but +0.0f, and copies only those:
+                                        * ba_step_out.waveout is NULL, ba_step_out.rows / row_of describe the packed rows (a consumer writes
+                                        * silence for row_of < 0, where it would have copied the row).  Decided on the data, never on the
+                                        * squelch state; iq_out, trace, status and the mixers are returned as without the flag. */
 
 /* trace byte layout: bits 0-2 Squelch current_state_, bit 3 is_open(), bit 4 should_process_audio(),
  * bit 5 should_filter_sample() && needs_raw_iq (the sample went through derotation/LPF) */
@@ -181,6 +187,11 @@ typedef struct ba_step_out {
     const uint8_t* trace;  /* [channel][n_batches*wave_batch] decision trace, NULL unless BA_FLAG_TRACE */
     const ba_channel_status* status; /* [batch][channel] */
     uint64_t frames_done;  /* FFT frames consumed from this device's stream so far */
+    /* BA_FLAG_SKIP_SILENT_ROWS only (else NULL / 0): */
+    const float* rows;     /* [n_rows][wave_batch]: the rows of the whole step (all devices) that are not silence, packed */
+    const int32_t* row_of; /* [channel][max_batches_per_step] for this device: index into rows, or -1 = wave_batch samples of +0.0f */
+    uint32_t n_rows;
+    int32_t row_of_stride; /* = max_batches_per_step */
 } ba_step_out;
 
 /* What one ba_cuda_process() mixed for one mixer: the batches every unmasked input had delivered by the end of the step

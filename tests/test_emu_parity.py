@@ -209,3 +209,23 @@ def test_emu_two_engines_on_two_devices_in_one_process(emu, monkeypatch):
     a, b = res[0][0]["waveout"], res[1][0]["waveout"]
     assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
     assert res[0][0]["frames_done"] == res[1][0]["frames_done"] > 0
+
+
+def test_emu_skip_silent_rows(emu):
+    """BA_FLAG_SKIP_SILENT_ROWS: only the (channel, batch) rows that hold anything but +0.0f come back, with a map; put back
+    together they are the audio of a run without the flag, bit for bit, and silence was in fact skipped."""
+    from boondock_airband_b200.engine import Engine
+    cfg, streams = scenarios.cfg1_short(0.9)
+    cfg.flags = 0
+    e = Engine(cfg, emu)
+    want = e.run_stream(streams, chunk_bytes=600_000)
+    e.close()
+    cfg2, _ = scenarios.cfg1_short(0.9)
+    cfg2.flags = abi.FLAG_SKIP_SILENT_ROWS
+    e = Engine(cfg2, emu)
+    got = e.run_stream(streams, chunk_bytes=450_001)
+    e.close()
+    assert got[0]["rows_skipped"] > 0
+    for c in range(len(cfg.devices[0].channels)):
+        assert np.array_equal(want[0]["waveout"][c].view(np.uint32), got[0]["waveout"][c].view(np.uint32))
+    assert got[0]["status"] == want[0]["status"]

@@ -525,3 +525,33 @@ def test_two_engines_on_two_gpus_in_one_process(cuda):
     for c in range(len(cfg0.devices[0].channels)):
         assert np.array_equal(r0[0]["waveout"][c].view(np.uint32), r1[0]["waveout"][c].view(np.uint32))
     assert r0[0]["frames_done"] == r1[0]["frames_done"] > 0
+
+
+@pytest.mark.parametrize("which", ["cfg1", "mixed", "multi"])
+def test_skip_silent_rows(cuda, which):
+    """BA_FLAG_SKIP_SILENT_ROWS: the packed rows and their map, put back together, are the audio of a run without the flag bit for
+    bit (plain and general channels, several inputs of different rates), and silent rows were in fact left out of the copy."""
+    if which == "cfg1":
+        cfg, streams = scenarios.cfg1_short(1.9)
+        cfg_b, _ = scenarios.cfg1_short(1.9)
+    elif which == "mixed":
+        cfg, streams = scenarios.mixed_options(1.5)
+        cfg_b, _ = scenarios.mixed_options(1.5)
+    else:
+        cfg, streams = scenarios.multi_device(0.9)
+        cfg_b, _ = scenarios.multi_device(0.9)
+    cfg.flags &= ~abi.FLAG_TRACE
+    cfg_b.flags = (cfg_b.flags & ~abi.FLAG_TRACE) | abi.FLAG_SKIP_SILENT_ROWS
+    e = Engine(cfg, cuda)
+    want = e.run_stream(streams, chunk_bytes=600_000)
+    e.close()
+    e = Engine(cfg_b, cuda)
+    got = e.run_stream(streams, chunk_bytes=450_001)
+    e.close()
+    assert sum(g["rows_skipped"] for g in got) > 0
+    for d in range(len(cfg.devices)):
+        for c in range(len(cfg.devices[d].channels)):
+            assert np.array_equal(want[d]["waveout"][c].view(np.uint32), got[d]["waveout"][c].view(np.uint32)), (d, c)
+        assert got[d]["status"] == want[d]["status"]
+        if want[d]["iq_out"] is not None:
+            assert np.array_equal(want[d]["iq_out"], got[d]["iq_out"])

@@ -164,14 +164,16 @@ def test_emu_demodulate_cuda_thread_body(oracle_built):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("which,chunk", [("cfg1", 262144), ("cfg1", 100_001), ("mixed", 65536), ("multi", 131072)])
-def test_demodulate_cuda_between_a_fake_rx_thread_and_a_fake_output_thread(shim, which, chunk):
+@pytest.mark.parametrize("which,chunk", [("cfg1", 262144), ("cfg1", 100_001), ("mixed", 65536), ("multi", 131072), ("cfg1_skip_silence", 200_000)])
+def test_demodulate_cuda_between_a_fake_rx_thread_and_a_fake_output_thread(shim, which, chunk, monkeypatch):
     """The audio the fake output thread takes out of channel_t::waveout equals, bit for bit, what Engine.run_stream produces from
     the same bytes through ba_cuda_submit; so do the per-batch indicators."""
     from boondock_airband_b200.engine import Engine
-    if which == "cfg1":
+    if which.startswith("cfg1"):
         cfg = configs.cfg1()
         streams = [synth.synth(cfg.devices[0], 2.2, 3, gate_on=0.4, gate_off=0.15)]
+        if which.endswith("skip_silence"):
+            monkeypatch.setenv("BA_CUDA_SKIP_SILENT_ROWS", "1")  # the thread body then asks for packed rows and writes silence itself
     elif which == "mixed":
         cfg, streams = scenarios.mixed_options(1.5, afc=False)
     else:
