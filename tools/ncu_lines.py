@@ -26,7 +26,10 @@ def line_table(cubin, kernel):
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
         if m:
-            line = int(m.group(2)) if m.group(1).endswith((".cu", ".h")) else line
+            if m.group(1).endswith(".cu"):
+                line = int(m.group(2))
+            elif m.group(1).endswith(".h") and "/csrc/" in m.group(1):
+                line = -int(m.group(2))  # a line of one of the kernel's own headers (ba_port.h ...): negative, so that ranges over the .cu leave it out
             continue
         m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
         if m:
@@ -47,6 +50,10 @@ def main():
     ia, isamp, iex = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")
     body = [r for r in rows[2:] if len(r) > iex and r[ia].startswith("0x")]
     base = int(body[0][ia], 16)
+    for i in range(1, len(body)):  # the page lists the kernel once per view (SASS, PTX-correlated ...): keep the first pass over the addresses
+        if int(body[i][ia], 16) < int(body[i - 1][ia], 16):
+            body = body[:i]
+            break
     table = line_table(a.cubin, a.kernel)
     per = {}
     tot_s = tot_e = 0
