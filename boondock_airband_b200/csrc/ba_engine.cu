@@ -1428,7 +1428,7 @@ int ba_cuda_process(ba_engine* e) {
             p.n_channels = e->total_channels;
             p.wave_batch = B;
             p.sincos = e->d_sincos;
-            int rc = k2_launch(p, e->n_plain, k2s, e->s_k2b, e->ev_fork, e->ev_join);
+            int rc = k2_launch(p, e->n_plain, e->sm_count, k2s, e->s_k2b, e->ev_fork, e->ev_join);
             if (rc != 0)
                 return fail(BA_ERR_CUDA, "demod launch: %s", cudaGetErrorString((cudaError_t)rc));
             e->launches += (e->n_plain > 0 ? 1 : 0) + (e->total_channels > e->n_plain ? 1 : 0);

@@ -160,7 +160,7 @@ struct K2Params {
 
 /* n_plain: the first n_plain slots of `order` are plain AM channels (demod_plain_kernel), the rest is general (one warp per
  * channel); s2/fork/join (optional) let the two kernels run concurrently */
-int k2_launch(const K2Params& p, int n_plain, cudaStream_t s, cudaStream_t s2, cudaEvent_t fork, cudaEvent_t join);
+int k2_launch(const K2Params& p, int n_plain, int sm_count, cudaStream_t s, cudaStream_t s2, cudaEvent_t fork, cudaEvent_t join);
 /* sets the demodulators' dynamic shared-memory limit on the CURRENT device; once per engine, after cudaSetDevice() */
 int k2_configure(void);
 
