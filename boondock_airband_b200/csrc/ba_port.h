@@ -14,6 +14,7 @@
             emu::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kern(__VA_ARGS__); }); \
     } while (0)
 #define BA_BAR_SYNC(id, count) emu::bar_named((id), (count))
+#define BA_CTA_SYNC_ONCE(id, threads) __syncthreads()
 /* cp.async: global -> shared without passing through registers; synchronous in the emulation */
 #define BA_CP_ASYNC_8(smem_ptr, gmem_ptr) memcpy((smem_ptr), (gmem_ptr), 8)
 #define BA_CP_ASYNC_4(smem_ptr, gmem_ptr) memcpy((smem_ptr), (gmem_ptr), 4)
@@ -46,6 +47,8 @@ static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
 #define BA_SHARED(name) extern __shared__ __align__(16) unsigned char name[]
 #define BA_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define BA_BAR_SYNC(id, count) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory")
+/* every thread of the CTA, before any subset starts using barrier `id` with its own count (a completed barrier can be reused with another count) */
+#define BA_CTA_SYNC_ONCE(id, threads) BA_BAR_SYNC((id), (threads))
 /* flags in shared memory that one warp of a CTA publishes and another polls (the chunk FIFO between the demodulator's stages):
  * release/acquire at CTA scope orders the slot's contents with the counter */
 static __device__ __forceinline__ int ba_flag_load(const int* p) {

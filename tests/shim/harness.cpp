@@ -49,6 +49,7 @@ struct Taken {
 };
 std::vector<std::vector<Taken> > g_taken;
 std::atomic<long> g_batches(0);
+long g_expected = 0; /* hand-offs the streams of this run amount to (all devices); 0 = unknown */
 volatile int g_stop_output = 0;
 
 /* circbuffer_append(), input-helpers.cpp:37-63 */
@@ -234,10 +235,11 @@ __attribute__((visibility("default"))) int ba_shim_run(const ba_engine_desc* des
     int rc = do_exit ? -101 : 0;
     for (Feed* f : feeds)
         pthread_join(f->in->rx_thread, NULL);
-    /* everything is in the rings: wait until the hand-offs stop coming */
+    /* everything is in the rings: wait until the hand-offs the streams amount to have been taken (bounded: 120 s without a new
+     * one), or, if the caller did not say how many that is, until they have stopped coming for two seconds */
     long seen = -1;
     int quiet = 0;
-    while (!do_exit && quiet < 40) {
+    while (!do_exit && (g_expected > 0 ? (g_batches < g_expected && quiet < 12000) : quiet < 200)) {
         usleep(10000);
         const long now = g_batches;
         quiet = (now == seen) ? quiet + 1 : 0;
@@ -257,6 +259,7 @@ __attribute__((visibility("default"))) int ba_shim_run(const ba_engine_desc* des
 }
 
 __attribute__((visibility("default"))) long ba_shim_batches(void) { return g_batches; }
+__attribute__((visibility("default"))) void ba_shim_expect_batches(long n) { g_expected = n; }
 __attribute__((visibility("default"))) size_t ba_shim_wave(int dev, int ch, const float** data) {
     *data = g_taken[dev][ch].wave.data();
     return g_taken[dev][ch].wave.size();

@@ -112,6 +112,9 @@ def run_shim(L, cfg, streams, chunk):
     views = [np.ascontiguousarray(s).view(np.uint8).reshape(-1) for s in streams]
     ptrs = (C.c_void_p * len(views))(*[v.ctypes.data for v in views])
     sizes = (C.c_size_t * len(views))(*[v.size for v in views])
+    # the harness stops the threads once this many hand-offs have been taken (not after a quiet spell: a loaded box makes those)
+    L.ba_shim_expect_batches.argtypes = [C.c_long]
+    L.ba_shim_expect_batches(sum(cfg.batches_for(d, v.size) for d, v in enumerate(views)))
     rc = L.ba_shim_run(C.byref(desc), ptrs, sizes, chunk)
     assert rc == 0, rc
     out = []
