@@ -276,7 +276,9 @@ BA_API int ba_cuda_process(ba_engine* e);
 BA_API int ba_cuda_collect(ba_engine* e, int ticket, int dev, ba_step_out* out);
 /* Same for mixer `mixer` of the engine descriptor: what mixer_thread would hand to the output thread (src/mixer.cpp:166-257). */
 BA_API int ba_cuda_collect_mixer(ba_engine* e, int ticket, int mixer, ba_mixer_out* out);
-/* mixer_disable_input() (src/mixer.cpp:96-112): a masked input is neither waited for nor summed.  enabled != 0 unmasks. */
+/* mixer_disable_input() (src/mixer.cpp:96-112): enabled == 0 masks the input - it is neither waited for nor summed from the next
+ * ba_cuda_process() on.  There is no way back, as in the reference (it has no mixer_enable_input()): enabled != 0 on an input that is
+ * masked returns BA_ERR_STATE; on one that is not it changes nothing. */
 BA_API int ba_cuda_mixer_input_mask(ba_engine* e, int mixer, int input, int enabled);
 /* Scan mode (row f-3): what controller_thread's `channels[0].freq_idx = i` does (src/boondock_airband.cpp:101-139): from the
  * next ba_cuda_process() on, the channel runs with freqlist[freq_idx] — its own Squelch, filters, AGC level, modulation,
