@@ -334,3 +334,36 @@ def check_demod_exact(cfg: abi.EngineCfg, streams, lib: str, frames_per_call: in
     finally:
         e.close()
     return compare_streams(cfg, o, res, exact=True)
+
+
+def squelch_regimes(o: Oracle, cfg: abi.EngineCfg, dev: int = 0):
+    """What the oracle's decision trace says the scenario exercised, per channel: the longest stretch of samples that were
+    filtered while the squelch stayed CLOSED ("held" by the filtered average), the samples filtered in OPENING, the longest
+    LOW_SIGNAL_ABORT stretch, and the number of OPENING episodes."""
+    out = []
+    for c in range(len(cfg.devices[dev].channels)):
+        tr = o.trace(dev, c)
+        st, fil = tr & abi.TRACE_STATE_MASK, (tr & abi.TRACE_FILTERED) != 0
+
+        def longest(mask):
+            edges = np.flatnonzero(np.diff(np.concatenate(([0], mask.astype(np.int8), [0]))))
+            return int((edges[1::2] - edges[::2]).max()) if edges.size else 0
+
+        opening = st == abi.SQ_OPENING
+        out.append(dict(held=longest((st == abi.SQ_CLOSED) & fil), opening_filtered=int((opening & fil).sum()),
+                        aborted=longest(st == abi.SQ_LOW_SIGNAL_ABORT), openings=int(np.count_nonzero(opening[1:] & ~opening[:-1]))))
+    return out
+
+
+def require_squelch_regimes(cfg: abi.EngineCfg, streams):
+    """The scenario does what it is for (checked on the oracle, so that a green parity test means the paths were walked)."""
+    o = Oracle(cfg)
+    o.feed(0, streams[0])
+    reg = squelch_regimes(o, cfg)
+    assert max(r["held"] for r in reg) >= 2000, reg             # a whole transmission held CLOSED, every sample filtered
+    assert sum(r["held"] >= 500 for r in reg) >= 3, reg
+    assert max(r["openings"] for r in reg) >= 8, reg             # one channel flaps CLOSED -> OPENING -> CLOSED
+    assert max(r["opening_filtered"] for r in reg) >= 1500, reg
+    assert sum(r["aborted"] >= 100 for r in reg) >= 4, reg       # most channels sit out a LOW_SIGNAL_ABORT
+    o.close()
+    return reg

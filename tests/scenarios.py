@@ -75,6 +75,27 @@ def afc_walk(seconds=1.6):
     return cfg, [iq]
 
 
+def held_by_post_filter(seconds=1.2, fm_demod=abi.FM_FAST_ATAN2):
+    """NFM channels through the low-pass, tuned a little off their carriers (still inside the carrier's bin): the raw magnitude
+    says "signal", the derotated carrier sits at 0.6-2 kHz where the narrow low-pass takes more than a tenth of it away, and the
+    filtered average never reaches 0.9 x the raw one (Squelch::buffer_[tail]).  The reference then either keeps the squelch
+    CLOSED for the whole transmission while filtering every sample (the open request is taken back within the sample,
+    squelch.cpp:223-232 with :268-274), or flaps CLOSED -> OPENING -> CLOSED, or opens late - one channel of each kind, plus one
+    on its carrier.  Transmitters by one configuration, receiver by another (as afc_walk)."""
+    fs, cf = 2_400_000, 145_000_000
+    ks = range(-3, 4)
+    offs = [0, 600, 900, 1200, 900, 1500, 2000]
+    bws = [12_500, 4000, 4000, 4000, 2000, 6000, 6000]
+    tx = DeviceCfg(sample_rate=fs, centerfreq=cf, sample_format="s16", channels=[ChannelCfg(freq=cf + 100_000 * k, modulation="nfm") for k in ks])
+    rx_ch = [ChannelCfg(freq=cf + 100_000 * k + offs[i], modulation="nfm", bandwidth=bws[i]) for i, k in enumerate(ks)]
+    rx_ch[2].ctcss = 100.0
+    rx_ch[3].notch = 100.0
+    rx = DeviceCfg(sample_rate=fs, centerfreq=cf, sample_format="s16", channels=rx_ch)
+    cfg = EngineCfg(fft_size=1024, wave_rate=16000, fm_demod=fm_demod, devices=[rx], flags=abi.FLAG_TRACE, max_batches_per_step=2)
+    iq = synth.synth(tx, seconds, 5, gate_on=0.45, gate_off=0.15)
+    return cfg, [iq]
+
+
 def multi_device(seconds=0.5):
     """Three inputs of different sample formats and rates behind one engine (device_start..device_end of one demod thread)."""
     devs = []

@@ -82,6 +82,15 @@ def test_emu_mixed_options_exact(emu, fm_demod):
     parity.check_demod_exact(cfg, streams, emu, frames_per_call=1777)
 
 
+def test_emu_squelch_held_by_the_filtered_average_exact(emu):
+    """The chunk-at-a-time paths of the general demodulator for a squelch that only counts - held CLOSED while every sample is
+    filtered, OPENING (with and without the filtered average running), LOW_SIGNAL_ABORT - against the sequential loop, bit for
+    bit (audio, per-sample decisions, counters), on a scenario the oracle's trace shows to spend thousands of samples in each."""
+    cfg, streams = scenarios.held_by_post_filter(1.0)
+    parity.require_squelch_regimes(cfg, streams)
+    parity.check_demod_exact(cfg, streams, emu, frames_per_call=2111)
+
+
 def test_emu_mixed_options_end_to_end(emu):
     cfg, streams = scenarios.mixed_options(0.7)
     o, res, _ = parity.run_both(cfg, streams, emu, chunk_bytes=555_555)

@@ -137,6 +137,17 @@ def test_demod_bit_exact(cuda, fm_demod):
     parity.check_demod_exact(cfg, streams, cuda, frames_per_call=3777)
 
 
+@pytest.mark.parametrize("fm_demod", [abi.FM_FAST_ATAN2, abi.FM_QUADRI_DEMOD])
+def test_demod_bit_exact_squelch_held_by_the_filtered_average(cuda, fm_demod):
+    """The chunk-at-a-time paths for a squelch that only counts (held CLOSED with every sample filtered, OPENING, LOW_SIGNAL_ABORT)
+    against the oracle's sequential loop, bit for bit; the oracle's trace is required to show thousands of samples in each."""
+    cfg, streams = scenarios.held_by_post_filter(1.6, fm_demod=fm_demod)
+    parity.require_squelch_regimes(cfg, streams)
+    parity.check_demod_exact(cfg, streams, cuda, frames_per_call=3333)
+    cfg.flags = 0  # and without the trace (the stores of the silent kinds differ)
+    parity.check_demod_exact(cfg, streams, cuda, frames_per_call=2000)
+
+
 def test_demod_bit_exact_cfg2(cuda):
     cfg, streams = scenarios.cfg2_small(16, 1.6)
     parity.check_demod_exact(cfg, streams, cuda, frames_per_call=3000)
