@@ -156,6 +156,7 @@ struct K2Params {
     int32_t wave_batch;   /* B, a multiple of 4 */
     const float* sincos;  /* [2][257] sin then cos, util.cpp:103-110 */
     int32_t first_slot, end_slot; /* filled by k2_launch: the slots of `order` this kernel covers */
+    int32_t plain_lanes;          /* filled by k2_launch: channels per CTA of demod_plain_kernel (1..32) */
 };
 
 /* n_plain: the first n_plain slots of `order` are plain AM channels (demod_plain_kernel), the rest is general (one warp per
