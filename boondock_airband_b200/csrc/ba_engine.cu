@@ -208,8 +208,6 @@ struct ba_engine {
     std::vector<float> window;
     ba::K2Chan* d_chan = nullptr;
     ba::K2State* d_state = nullptr;
-    ba::K2ChainRec* d_chain_rec = nullptr; /* chain pass records (configurations with many general channels), else NULL */
-    int chain_chunks = 0;
     ba::K2Ctcss* d_ctcss = nullptr;
     int32_t* d_order = nullptr;
     uint32_t* d_tile_counter = nullptr;
@@ -328,7 +326,6 @@ void free_engine(ba_engine* e) {
     cudaFree(e->d_sincos);
     cudaFree(e->d_chan);
     cudaFree(e->d_state);
-    cudaFree(e->d_chain_rec);
     cudaFree(e->d_ctcss);
     cudaFree(e->d_order);
     cudaFree(e->d_tile_counter);
@@ -769,12 +766,6 @@ int ba_cuda_create(const ba_engine_desc* desc, ba_engine** out) {
         for (int i = 0; i < TC; i++)
             e->n_plain += plain(i) ? 1 : 0;
         CU(cudaMemcpy(e->d_order, order.data(), sizeof(int32_t) * TC, cudaMemcpyHostToDevice));
-        /* many general channels: their moving averages run in a pass of their own, a lane per channel (demod.cu, chain_pass_kernel) */
-        const int n_full = TC - e->n_plain;
-        if (n_full > 0 && n_full >= k2_chain_pass_min(e->sm_count)) {
-            e->chain_chunks = k2_chain_chunks(e->max_batches, e->B);
-            CU(cudaMalloc((void**)&e->d_chain_rec, sizeof(K2ChainRec) * (size_t)n_full * e->chain_chunks));
-        }
     }
     CU(cudaMemcpy(e->d_chan, e->h_chan.data(), sizeof(K2Chan) * TC, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(e->d_state, h_state.data(), sizeof(K2State) * TC, cudaMemcpyHostToDevice));
@@ -1437,12 +1428,10 @@ int ba_cuda_process(ba_engine* e) {
             p.n_channels = e->total_channels;
             p.wave_batch = B;
             p.sincos = e->d_sincos;
-            p.chain_rec = e->d_chain_rec;
-            p.chain_chunks = e->chain_chunks;
             int rc = k2_launch(p, e->n_plain, e->sm_count, k2s, e->s_k2b, e->ev_fork, e->ev_join);
             if (rc != 0)
                 return fail(BA_ERR_CUDA, "demod launch: %s", cudaGetErrorString((cudaError_t)rc));
-            e->launches += (e->n_plain > 0 ? 1 : 0) + (e->total_channels > e->n_plain ? 1 : 0) + (e->d_chain_rec ? 1 : 0);
+            e->launches += (e->n_plain > 0 ? 1 : 0) + (e->total_channels > e->n_plain ? 1 : 0);
         }
         CU(cudaEventRecord(s.ev_k[4 * ph + 3], k2s));
     }

@@ -131,19 +131,6 @@ struct alignas(16) K2State {
     float lxr0, lxr1, lxr2, lxi0, lxi1, lxi2, lyr0, lyr1, lyr2, lyi0, lyi1, lyi2;
     float ring[BA_SQ_RING];    /* Squelch::buffer_ */
     float wavein_hist[BA_E];   /* wavein[] as the loop left it for the last E frames (.cpp:548 overwrites it) */
-    /* noise and pre_cap as the launch found them, left here by chain_pass_kernel (which runs the launch's moving averages ahead of
-     * demod_full_kernel and writes their end values back before that kernel reads the state); transient within a launch */
-    float chain_noise0, chain_pre_cap0;
-};
-
-/* What the chain of one general channel leaves per chunk of 32 samples (chain_pass_kernel -> demod_full_kernel through HBM, or the
- * chain warp -> the squelch stage through shared memory: the tail of GenChainSlot): pre_filter_.capped_ after update_moving_avg per
- * sample, noise_floor_ in force per quad, pre_filter_.full_ after the chunk. */
-struct alignas(16) K2ChainRec {
-    float p[32];
-    float nz[8];
-    float pf;
-    float pad[3];
 };
 
 /* per input, per launch */
@@ -170,19 +157,11 @@ struct K2Params {
     const float* sincos;  /* [2][257] sin then cos, util.cpp:103-110 */
     int32_t first_slot, end_slot; /* filled by k2_launch: the slots of `order` this kernel covers */
     int32_t plain_lanes;          /* filled by k2_launch: channels per CTA of demod_plain_kernel (1..32) */
-    /* chain pass (launches with many general channels): [general channel in launch order][chain_chunks] or NULL */
-    K2ChainRec* chain_rec;
-    int32_t chain_chunks;
 };
 
 /* n_plain: the first n_plain slots of `order` are plain AM channels (demod_plain_kernel), the rest is general (one warp per
  * channel); s2/fork/join (optional) let the two kernels run concurrently */
 int k2_launch(const K2Params& p, int n_plain, int sm_count, cudaStream_t s, cudaStream_t s2, cudaEvent_t fork, cudaEvent_t join);
-/* General channels from which on a launch runs their moving averages in chain_pass_kernel (a lane per channel) instead of in a warp
- * of every channel's CTA: more than the GPU holds at three CTAs per SM (BA_CUDA_K2_CHAIN_PASS_MIN overrides: tests, tuning). */
-int k2_chain_pass_min(int sm_count);
-/* records per general channel for launches of up to max_batches batches of B samples */
-int k2_chain_chunks(int max_batches, int B);
 /* sets the demodulators' dynamic shared-memory limit on the CURRENT device; once per engine, after cudaSetDevice() */
 int k2_configure(void);
 

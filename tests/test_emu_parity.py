@@ -91,25 +91,6 @@ def test_emu_squelch_held_by_the_filtered_average_exact(emu):
     parity.check_demod_exact(cfg, streams, emu, frames_per_call=2111)
 
 
-@pytest.mark.parametrize("which", ["mixed", "held", "scan"])
-def test_emu_chain_pass_exact(emu, monkeypatch, which):
-    """Launches with many general channels run the channels' moving averages in chain_pass_kernel (a lane per channel, records
-    through HBM) instead of in a warp of every channel's CTA; forced here for a handful of channels: the same bits come out
-    (audio, decisions, levels, counters; ragged calls, several launches, a scan channel switching frequency between them)."""
-    monkeypatch.setenv("BA_CUDA_K2_CHAIN_PASS_MIN", "1")
-    if which == "mixed":
-        cfg, streams = scenarios.mixed_options(0.7, afc=False)
-        parity.check_demod_exact(cfg, streams, emu, frames_per_call=1777)
-    elif which == "held":
-        cfg, streams = scenarios.held_by_post_filter(0.8)
-        parity.check_demod_exact(cfg, streams, emu, frames_per_call=2111)
-    else:
-        cfg, streams = scenarios.scan_mode(1.3)
-        o, res, plan, _ = parity.run_scan(cfg, streams, emu, every=2, order=[0, 1, 2, 1, 0, 2])
-        assert len(plan) >= 4
-        parity.compare_streams(cfg, o, res, min_open=1000)
-
-
 def test_emu_mixed_options_end_to_end(emu):
     cfg, streams = scenarios.mixed_options(0.7)
     o, res, _ = parity.run_both(cfg, streams, emu, chunk_bytes=555_555)

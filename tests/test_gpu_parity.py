@@ -148,21 +148,6 @@ def test_demod_bit_exact_squelch_held_by_the_filtered_average(cuda, fm_demod):
     parity.check_demod_exact(cfg, streams, cuda, frames_per_call=2000)
 
 
-@pytest.mark.parametrize("which", ["mixed", "held", "cfg2"])
-def test_chain_pass_bit_exact(cuda, monkeypatch, which):
-    """chain_pass_kernel (the moving averages of a launch's general channels, a lane per channel, records through HBM - what
-    launches with more general channels than the GPU holds use) forced for a handful of channels: bit for bit the oracle's
-    audio, decisions, levels and counters, as with the chain warp inside every CTA."""
-    monkeypatch.setenv("BA_CUDA_K2_CHAIN_PASS_MIN", "1")
-    if which == "mixed":
-        cfg, streams = scenarios.mixed_options(1.5, afc=False)
-    elif which == "held":
-        cfg, streams = scenarios.held_by_post_filter(1.6)
-    else:
-        cfg, streams = scenarios.cfg2_small(16, 1.6)
-    parity.check_demod_exact(cfg, streams, cuda, frames_per_call=3111)
-
-
 def test_demod_bit_exact_cfg2(cuda):
     cfg, streams = scenarios.cfg2_small(16, 1.6)
     parity.check_demod_exact(cfg, streams, cuda, frames_per_call=3000)
